@@ -1,0 +1,85 @@
+"""ctypes binding of the C ABI declared in ``include/efgb200.h``.
+
+The library is the product: there is no CPU or PyTorch fallback.  ``lib()`` raises if
+``libefgb200.so`` has not been built (``python -m efg_b200._build`` or ``__graft_entry__.build()``).
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libefgb200.so")
+
+_vp = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_int = ctypes.c_int
+_sz = ctypes.c_size_t
+_host_i32x3 = ctypes.POINTER(ctypes.c_int32)
+_host_f32 = ctypes.POINTER(ctypes.c_float)
+
+# name -> (restype, argtypes); mirrors include/efgb200.h one to one
+SIGNATURES = {
+    "efgb_last_error": (ctypes.c_char_p, []),
+    "efgb_version": (_int, []),
+    "efgb_voxelize_workspace_bytes": (_sz, [_i64, _int]),
+    "efgb_hard_voxelize": (_int, [_vp, _i64, _int, _vp, _int, _host_f32, _host_f32, _int, _int,
+                                  _vp, _vp, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "efgb_dynamic_voxelize": (_int, [_vp, _i64, _int, _host_f32, _host_f32, _vp, _vp]),
+    "efgb_scatter_workspace_bytes": (_sz, [_i64, _host_i32x3]),
+    "efgb_scatter_phase1": (_int, [_vp, _i64, _host_i32x3, _vp, _vp, _sz, _vp]),
+    "efgb_scatter_phase2": (_int, [_vp, _vp, _i64, _int, _host_i32x3, _int, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "efgb_scatter_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _i64, _vp, _vp, _sz, _vp]),
+    "efgb_rulebook_workspace_bytes": (_sz, [_int, _host_i32x3, _i64]),
+    "efgb_subm_rulebook": (_int, [_vp, _i64, _int, _host_i32x3, _host_i32x3, _int, _vp, _vp, _sz, _vp]),
+    "efgb_sparse_rulebook_phase1": (_int, [_vp, _i64, _int, _host_i32x3, _host_i32x3, _host_i32x3, _host_i32x3,
+                                           _host_i32x3, _vp, _vp, _sz, _vp]),
+    "efgb_sparse_rulebook_phase2": (_int, [_vp, _i64, _int, _host_i32x3, _host_i32x3, _host_i32x3, _host_i32x3,
+                                           _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "efgb_spconv_forward": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _i64, _int, _int, _vp, _vp]),
+    "efgb_spconv_wgrad": (_int, [_vp, _i64, _int, _vp, _vp, _i64, _int, _int, _vp, _vp]),
+    "efgb_sparse_to_dense": (_int, [_vp, _vp, _i64, _int, _int, _host_i32x3, _vp, _vp]),
+    "efgb_dense_to_sparse": (_int, [_vp, _vp, _i64, _int, _int, _host_i32x3, _vp, _vp]),
+    "efgb_box_attn_forward": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _vp, _vp]),
+    "efgb_box_attn_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int,
+                                      _vp, _vp, _vp, _vp]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def lib():
+    """Return the loaded C-ABI library, loading it on first use.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    "efg_b200: %s is missing. The CUDA library is the only implementation of this "
+                    "path (no CPU fallback); build it with `python -m efg_b200._build`." % LIB_PATH
+                )
+            handle = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(handle, name)  # AttributeError if the .so is stale
+                fn.restype = res
+                fn.argtypes = args
+            _lib = handle
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().efgb_last_error().decode("utf-8", "replace")
+        raise RuntimeError("efg_b200 %s failed (code %d): %s" % (what, rc, msg))
+
+
+def i32x3(values):
+    a = (ctypes.c_int32 * 3)(*[int(v) for v in values])
+    return a
+
+
+def f32array(values):
+    a = (ctypes.c_float * len(values))(*[float(v) for v in values])
+    return a

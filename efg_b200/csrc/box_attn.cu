@@ -1,0 +1,296 @@
+// Box attention (multi-scale bilinear sample-and-weight), forward and backward, sm_100a.
+//
+// Same math as the reference kernels (efg/operators/src/box_attn/box_attn_kernel.cuh:35-98 fwd
+// bilinear, :101-190 bwd bilinear, :275-351 fwd loop) but a different mapping: the reference runs
+// one thread per output scalar (every thread of a head re-reads the same loc/attn scalars and
+// recomputes the same bilinear weights) and, in backward, one 32-thread block per (b,q,h) with a
+// thread-0 serial shared-memory reduction.  Here one WARP owns one (b,q,h): lanes are the head's
+// channels, so each bilinear corner is one coalesced 128-byte line, loc/attn are loaded once per
+// warp (lane p holds point p) and broadcast by shuffle, grad_loc/grad_attn are reduced with
+// shuffles, and grad_value is accumulated with one coalesced RED per corner.
+#include "common.cuh"
+
+namespace efgb {
+
+struct Corner {
+  int h_low, w_low;
+  float w1, w2, w3, w4;   // bilinear weights: (hl,wl) (hl,wh) (hh,wl) (hh,wh)
+  float lh, lw, hh, hw;
+  bool ok1, ok2, ok3, ok4;
+};
+
+__device__ __forceinline__ bool make_corner(float x, float y, int Hl, int Wl, Corner* c, float* h_im_out, float* w_im_out) {
+  // h_im = loc_y * H - 0.5 with the product rounded before the subtraction (box_attn_kernel.cuh:325-326)
+  const float h_im = __fsub_rn(__fmul_rn(y, static_cast<float>(Hl)), 0.5f);
+  const float w_im = __fsub_rn(__fmul_rn(x, static_cast<float>(Wl)), 0.5f);
+  *h_im_out = h_im;
+  *w_im_out = w_im;
+  if (!(h_im > -1.f && w_im > -1.f && h_im < static_cast<float>(Hl) && w_im < static_cast<float>(Wl))) return false;
+  const float hf = floorf(h_im), wf = floorf(w_im);
+  c->h_low = static_cast<int>(hf);
+  c->w_low = static_cast<int>(wf);
+  c->lh = h_im - hf;
+  c->lw = w_im - wf;
+  c->hh = 1.f - c->lh;
+  c->hw = 1.f - c->lw;
+  c->w1 = c->hh * c->hw;
+  c->w2 = c->hh * c->lw;
+  c->w3 = c->lh * c->hw;
+  c->w4 = c->lh * c->lw;
+  const bool hl = c->h_low >= 0, hh = c->h_low + 1 <= Hl - 1;
+  const bool wl = c->w_low >= 0, wh = c->w_low + 1 <= Wl - 1;
+  c->ok1 = hl && wl;
+  c->ok2 = hl && wh;
+  c->ok3 = hh && wl;
+  c->ok4 = hh && wh;
+  return true;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+// NC = ceil(head_dim / 32) channel slots per lane.
+template <int NC>
+__global__ void __launch_bounds__(256)
+box_attn_fwd_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
+                    const int64_t* __restrict__ level_start, const float* __restrict__ loc,
+                    const float* __restrict__ attn, int64_t num_warps, int len_value, int num_heads, int head_dim,
+                    int num_levels, int len_query, int num_points, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (idx >= num_warps) return;
+  const int h = static_cast<int>(idx % num_heads);
+  const int64_t b = idx / (static_cast<int64_t>(num_heads) * len_query);
+  const int64_t pix_stride = static_cast<int64_t>(num_heads) * head_dim;
+  const float* loc_q = loc + idx * num_levels * num_points * 2;
+  const float* attn_q = attn + idx * num_levels * num_points;
+
+  float acc[NC];
+#pragma unroll
+  for (int n = 0; n < NC; ++n) acc[n] = 0.f;
+
+  for (int l = 0; l < num_levels; ++l) {
+    const int Hl = static_cast<int>(shapes[2 * l]), Wl = static_cast<int>(shapes[2 * l + 1]);
+    const float* vbase = value + (b * len_value + level_start[l]) * pix_stride + static_cast<int64_t>(h) * head_dim;
+    for (int p0 = 0; p0 < num_points; p0 += 32) {
+      const int p = p0 + lane;
+      float lx = 0.f, ly = 0.f, wt = 0.f;
+      if (p < num_points) {
+        const float2 xy = *reinterpret_cast<const float2*>(loc_q + (l * num_points + p) * 2);
+        lx = xy.x;
+        ly = xy.y;
+        wt = attn_q[l * num_points + p];
+      }
+      const int np = min(32, num_points - p0);
+      for (int pp = 0; pp < np; ++pp) {
+        const float x = __shfl_sync(0xffffffffu, lx, pp);
+        const float y = __shfl_sync(0xffffffffu, ly, pp);
+        const float a = __shfl_sync(0xffffffffu, wt, pp);
+        Corner c;
+        float h_im, w_im;
+        if (!make_corner(x, y, Hl, Wl, &c, &h_im, &w_im)) continue;
+        const float* p1 = vbase + (static_cast<int64_t>(c.h_low) * Wl + c.w_low) * pix_stride;
+        const float* p2 = p1 + pix_stride;
+        const float* p3 = p1 + static_cast<int64_t>(Wl) * pix_stride;
+        const float* p4 = p3 + pix_stride;
+#pragma unroll
+        for (int n = 0; n < NC; ++n) {
+          const int ch = lane + 32 * n;
+          if (ch < head_dim) {
+            const float v1 = c.ok1 ? __ldg(p1 + ch) : 0.f;
+            const float v2 = c.ok2 ? __ldg(p2 + ch) : 0.f;
+            const float v3 = c.ok3 ? __ldg(p3 + ch) : 0.f;
+            const float v4 = c.ok4 ? __ldg(p4 + ch) : 0.f;
+            const float val = c.w1 * v1 + c.w2 * v2 + c.w3 * v3 + c.w4 * v4;
+            acc[n] += val * a;
+          }
+        }
+      }
+    }
+  }
+  float* o = out + idx * head_dim;
+#pragma unroll
+  for (int n = 0; n < NC; ++n) {
+    const int ch = lane + 32 * n;
+    if (ch < head_dim) o[ch] = acc[n];
+  }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(256)
+box_attn_bwd_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
+                    const int64_t* __restrict__ level_start, const float* __restrict__ loc,
+                    const float* __restrict__ attn, const float* __restrict__ grad_out, int64_t num_warps,
+                    int len_value, int num_heads, int head_dim, int num_levels, int len_query, int num_points,
+                    float* __restrict__ grad_value, float* __restrict__ grad_loc, float* __restrict__ grad_attn) {
+  const int lane = threadIdx.x & 31;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (idx >= num_warps) return;
+  const int h = static_cast<int>(idx % num_heads);
+  const int64_t b = idx / (static_cast<int64_t>(num_heads) * len_query);
+  const int64_t pix_stride = static_cast<int64_t>(num_heads) * head_dim;
+  const int64_t lp = static_cast<int64_t>(num_levels) * num_points;
+  const float* loc_q = loc + idx * lp * 2;
+  const float* attn_q = attn + idx * lp;
+  float* gloc_q = grad_loc + idx * lp * 2;
+  float* gattn_q = grad_attn + idx * lp;
+
+  float tg[NC];
+#pragma unroll
+  for (int n = 0; n < NC; ++n) {
+    const int ch = lane + 32 * n;
+    tg[n] = ch < head_dim ? grad_out[idx * head_dim + ch] : 0.f;
+  }
+
+  for (int l = 0; l < num_levels; ++l) {
+    const int Hl = static_cast<int>(shapes[2 * l]), Wl = static_cast<int>(shapes[2 * l + 1]);
+    const int64_t voff = (b * len_value + level_start[l]) * pix_stride + static_cast<int64_t>(h) * head_dim;
+    const float* vbase = value + voff;
+    float* gbase = grad_value + voff;
+    for (int p0 = 0; p0 < num_points; p0 += 32) {
+      const int p = p0 + lane;
+      float lx = 0.f, ly = 0.f, wt = 0.f;
+      if (p < num_points) {
+        const float2 xy = *reinterpret_cast<const float2*>(loc_q + (l * num_points + p) * 2);
+        lx = xy.x;
+        ly = xy.y;
+        wt = attn_q[l * num_points + p];
+      }
+      // per-point results gathered back to lane p for one coalesced store
+      float out_gx = 0.f, out_gy = 0.f, out_ga = 0.f;
+      const int np = min(32, num_points - p0);
+      for (int pp = 0; pp < np; ++pp) {
+        const float x = __shfl_sync(0xffffffffu, lx, pp);
+        const float y = __shfl_sync(0xffffffffu, ly, pp);
+        const float a = __shfl_sync(0xffffffffu, wt, pp);
+        Corner c;
+        float h_im, w_im;
+        if (!make_corner(x, y, Hl, Wl, &c, &h_im, &w_im)) continue;  // warp-uniform
+        const int64_t o1 = (static_cast<int64_t>(c.h_low) * Wl + c.w_low) * pix_stride;
+        const int64_t o2 = o1 + pix_stride;
+        const int64_t o3 = o1 + static_cast<int64_t>(Wl) * pix_stride;
+        const int64_t o4 = o3 + pix_stride;
+        float s_val = 0.f, s_gw = 0.f, s_gh = 0.f;
+#pragma unroll
+        for (int n = 0; n < NC; ++n) {
+          const int ch = lane + 32 * n;
+          if (ch < head_dim) {
+            const float tgv = tg[n] * a;  // top_grad * attn_weight
+            float gh = 0.f, gw = 0.f;
+            float v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f;
+            if (c.ok1) {
+              v1 = __ldg(vbase + o1 + ch);
+              gh -= c.hw * v1;
+              gw -= c.hh * v1;
+              atomicAdd(gbase + o1 + ch, c.w1 * tgv);
+            }
+            if (c.ok2) {
+              v2 = __ldg(vbase + o2 + ch);
+              gh -= c.lw * v2;
+              gw += c.hh * v2;
+              atomicAdd(gbase + o2 + ch, c.w2 * tgv);
+            }
+            if (c.ok3) {
+              v3 = __ldg(vbase + o3 + ch);
+              gh += c.hw * v3;
+              gw -= c.lh * v3;
+              atomicAdd(gbase + o3 + ch, c.w3 * tgv);
+            }
+            if (c.ok4) {
+              v4 = __ldg(vbase + o4 + ch);
+              gh += c.lw * v4;
+              gw += c.lh * v4;
+              atomicAdd(gbase + o4 + ch, c.w4 * tgv);
+            }
+            const float val = c.w1 * v1 + c.w2 * v2 + c.w3 * v3 + c.w4 * v4;
+            s_val += tg[n] * val;
+            s_gw += static_cast<float>(Wl) * gw * tgv;
+            s_gh += static_cast<float>(Hl) * gh * tgv;
+          }
+        }
+        s_val = warp_sum(s_val);
+        s_gw = warp_sum(s_gw);
+        s_gh = warp_sum(s_gh);
+        if (lane == pp) {
+          out_ga = s_val;
+          out_gx = s_gw;
+          out_gy = s_gh;
+        }
+      }
+      if (p < num_points) {
+        *reinterpret_cast<float2*>(gloc_q + (l * num_points + p) * 2) = make_float2(out_gx, out_gy);
+        gattn_q[l * num_points + p] = out_ga;
+      }
+    }
+  }
+}
+
+static int check_args(int batch, int len_value, int num_heads, int head_dim, int num_levels, int len_query,
+                      int num_points, const char* who) {
+  EFGB_REQUIRE(batch >= 0 && len_value >= 0 && num_heads >= 1 && head_dim >= 1 && num_levels >= 1 && len_query >= 0 &&
+                   num_points >= 1,
+               EFGB_EINVAL, "%s: bad shape", who);
+  EFGB_REQUIRE(head_dim <= 128, EFGB_EINVAL, "%s: head_dim %d > 128 is not supported", who, head_dim);
+  return EFGB_OK;
+}
+
+}  // namespace efgb
+
+using namespace efgb;
+
+extern "C" int efgb_box_attn_forward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start,
+                                     const float* loc, const float* attn, int batch, int len_value, int num_heads,
+                                     int head_dim, int num_levels, int len_query, int num_points, float* out,
+                                     efgb_stream_t stream_) {
+  cudaStream_t stream = as_stream(stream_);
+  int rc = check_args(batch, len_value, num_heads, head_dim, num_levels, len_query, num_points, "box_attn_forward");
+  if (rc != EFGB_OK) return rc;
+  const int64_t nw = static_cast<int64_t>(batch) * len_query * num_heads;
+  if (nw == 0) return EFGB_OK;
+  EFGB_REQUIRE(value && spatial_shapes && level_start && loc && attn && out, EFGB_EINVAL, "box_attn_forward: null pointer");
+  const unsigned nb = static_cast<unsigned>((nw + 7) / 8);
+  const int nc = (head_dim + 31) / 32;
+#define EFGB_FWD(NC)                                                                                              \
+  box_attn_fwd_kernel<NC><<<nb, 256, 0, stream>>>(value, spatial_shapes, level_start, loc, attn, nw, len_value,   \
+                                                  num_heads, head_dim, num_levels, len_query, num_points, out)
+  if (nc == 1) EFGB_FWD(1);
+  else if (nc == 2) EFGB_FWD(2);
+  else EFGB_FWD(4);
+#undef EFGB_FWD
+  EFGB_LAUNCH_OK("box_attn_fwd_kernel");
+  return EFGB_OK;
+}
+
+extern "C" int efgb_box_attn_backward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start,
+                                      const float* loc, const float* attn, const float* grad_out, int batch,
+                                      int len_value, int num_heads, int head_dim, int num_levels, int len_query,
+                                      int num_points, float* grad_value, float* grad_loc, float* grad_attn,
+                                      efgb_stream_t stream_) {
+  cudaStream_t stream = as_stream(stream_);
+  int rc = check_args(batch, len_value, num_heads, head_dim, num_levels, len_query, num_points, "box_attn_backward");
+  if (rc != EFGB_OK) return rc;
+  const size_t vbytes = static_cast<size_t>(batch) * len_value * num_heads * head_dim * sizeof(float);
+  if (vbytes) {
+    EFGB_REQUIRE(grad_value, EFGB_EINVAL, "box_attn_backward: null grad_value");
+    EFGB_CUDA_OK(cudaMemsetAsync(grad_value, 0, vbytes, stream));
+  }
+  const int64_t nw = static_cast<int64_t>(batch) * len_query * num_heads;
+  if (nw == 0) return EFGB_OK;
+  EFGB_REQUIRE(value && spatial_shapes && level_start && loc && attn && grad_out && grad_loc && grad_attn, EFGB_EINVAL,
+               "box_attn_backward: null pointer");
+  const unsigned nb = static_cast<unsigned>((nw + 7) / 8);
+  const int nc = (head_dim + 31) / 32;
+#define EFGB_BWD(NC)                                                                                               \
+  box_attn_bwd_kernel<NC><<<nb, 256, 0, stream>>>(value, spatial_shapes, level_start, loc, attn, grad_out, nw,     \
+                                                  len_value, num_heads, head_dim, num_levels, len_query, num_points, \
+                                                  grad_value, grad_loc, grad_attn)
+  if (nc == 1) EFGB_BWD(1);
+  else if (nc == 2) EFGB_BWD(2);
+  else EFGB_BWD(4);
+#undef EFGB_BWD
+  EFGB_LAUNCH_OK("box_attn_bwd_kernel");
+  return EFGB_OK;
+}

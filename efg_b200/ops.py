@@ -1,0 +1,313 @@
+"""Tensor-level wrappers over the C ABI (``include/efgb200.h``).
+
+PyTorch is used only as the owner of device memory and streams: every function validates its
+tensors the way the reference's ``CHECK_INPUT`` does (CUDA + contiguous,
+efg/operators/src/utils/efg_cutils.h:12-15), allocates outputs and the scratch workspace, and
+enqueues the CUDA kernels on the current stream.  There is no CPU path: CPU tensors raise
+``RuntimeError`` exactly where the reference raises "Not compiled with GPU support" /
+"Not implemented on the CPU" (voxelization.h:63, box_attn.h:53).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_REDUCE = {"sum": 0, "mean": 1, "max": 2}
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _check(t, name, dtype=None):
+    if not isinstance(t, torch.Tensor):
+        raise RuntimeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor (efg_b200 has no CPU implementation)" % name)
+    if not t.is_contiguous():
+        raise RuntimeError("%s must be contiguous" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError("%s must have dtype %s, got %s" % (name, dtype, t.dtype))
+
+
+_workspaces = {}
+
+
+def workspace(nbytes, device):
+    """Per-(device, stream) scratch buffer that only ever grows."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+# --------------------------------------------------------------------------------------------
+# voxelizer
+# --------------------------------------------------------------------------------------------
+def hard_voxelize_batched(points, scene_offsets, voxel_size, coors_range, max_points, max_voxels,
+                          coors_dim=4, want_voxels=True, want_mean=True, capacity=None):
+    """Voxelize a batch of scenes in one pass.
+
+    points [N,F] f32 (scenes concatenated), scene_offsets [B+1] i32 on device.
+    Returns dict(voxels, coors, num_points_per_voxel, mean, counts) with buffers of `capacity`
+    rows; `counts` is a device i32 [B+1] (per-scene count, total) — the caller decides when to
+    synchronise on it.
+    """
+    _check(points, "points", torch.float32)
+    _check(scene_offsets, "scene_offsets", torch.int32)
+    if points.dim() != 2:
+        raise RuntimeError("points must be [N, F]")
+    n, f = points.shape
+    batch = scene_offsets.numel() - 1
+    if capacity is None:
+        capacity = n if max_voxels < 0 else min(n, batch * max_voxels)
+    capacity = max(int(capacity), 1)
+    dev = points.device
+    L = _lib.lib()
+    voxels = torch.empty((capacity, max_points, f), dtype=torch.float32, device=dev) if want_voxels else None
+    coors = torch.empty((capacity, coors_dim), dtype=torch.int32, device=dev)
+    npv = torch.empty((capacity,), dtype=torch.int32, device=dev)
+    mean = torch.empty((capacity, f), dtype=torch.float32, device=dev) if want_mean else None
+    counts = torch.empty((batch + 1,), dtype=torch.int32, device=dev)
+    wsb = L.efgb_voxelize_workspace_bytes(n, batch)
+    ws = workspace(wsb, dev)
+    rc = L.efgb_hard_voxelize(_p(points), n, f, _p(scene_offsets), batch, _lib.f32array(voxel_size),
+                              _lib.f32array(coors_range), int(max_points), int(max_voxels), _p(voxels), _p(coors),
+                              int(coors_dim), _p(npv), _p(mean), _p(counts), _p(ws), ws.numel(), _stream())
+    _lib.check(rc, "hard_voxelize")
+    return {"voxels": voxels, "coors": coors, "num_points_per_voxel": npv, "mean": mean, "counts": counts}
+
+
+def dynamic_voxelize(points, coors, voxel_size, coors_range):
+    _check(points, "points", torch.float32)
+    _check(coors, "coors", torch.int32)
+    L = _lib.lib()
+    rc = L.efgb_dynamic_voxelize(_p(points), points.shape[0], points.shape[1], _lib.f32array(voxel_size),
+                                 _lib.f32array(coors_range), _p(coors), _stream())
+    _lib.check(rc, "dynamic_voxelize")
+
+
+# --------------------------------------------------------------------------------------------
+# dynamic scatter
+# --------------------------------------------------------------------------------------------
+def dynamic_scatter_forward(feats, coors, reduce_type):
+    _check(feats, "feats", torch.float32)
+    _check(coors, "coors", torch.int32)
+    if coors.dim() != 2 or coors.shape[1] != 3:
+        raise RuntimeError("coors must be [N, 3]")
+    if reduce_type not in _REDUCE:
+        raise RuntimeError("reduce_type must be one of sum/mean/max, got %r" % (reduce_type,))
+    n, c = feats.shape
+    dev = feats.device
+    L = _lib.lib()
+    if n == 0:
+        return (feats.new_zeros((0, c)), coors.new_zeros((0, 3)), coors.new_zeros((0,)), coors.new_zeros((0,)))
+    # extent of the coordinate space, as the reference: coors.max(0) + 1 (scatter_points_cuda.cu:220)
+    dims_t = (coors.max(0)[0] + 1).clamp_(min=1).cpu()
+    dims = _lib.i32x3(dims_t.tolist())
+    ws = workspace(L.efgb_scatter_workspace_bytes(n, dims), dev)
+    m_dev = torch.zeros((1,), dtype=torch.int32, device=dev)
+    _lib.check(L.efgb_scatter_phase1(_p(coors), n, dims, _p(m_dev), _p(ws), ws.numel(), _stream()), "scatter_phase1")
+    m = int(m_dev.item())
+    voxel_feats = torch.empty((m, c), dtype=torch.float32, device=dev)
+    voxel_coors = torch.empty((m, 3), dtype=torch.int32, device=dev)
+    p2v = torch.empty((n,), dtype=torch.int32, device=dev)
+    count = torch.empty((m,), dtype=torch.int32, device=dev)
+    _lib.check(
+        L.efgb_scatter_phase2(_p(feats), _p(coors), n, c, dims, _REDUCE[reduce_type], m, _p(voxel_feats),
+                              _p(voxel_coors), _p(p2v), _p(count), _p(ws), ws.numel(), _stream()),
+        "scatter_phase2")
+    return voxel_feats, voxel_coors, p2v, count
+
+
+def dynamic_scatter_backward(grad_feats, grad_voxel_feats, feats, voxel_feats, p2v, count, reduce_type):
+    for t, nm in ((grad_feats, "grad_feats"), (grad_voxel_feats, "grad_reduced_feats"), (feats, "feats"),
+                  (voxel_feats, "reduced_feats"), (p2v, "coors_map"), (count, "reduce_count")):
+        _check(t, nm)
+    n, c = feats.shape
+    m = voxel_feats.shape[0]
+    L = _lib.lib()
+    ws = workspace(max(m * c * 4, 4), feats.device)
+    _lib.check(
+        L.efgb_scatter_backward(_p(grad_voxel_feats), _p(feats), _p(voxel_feats), _p(p2v), _p(count), n, c,
+                                _REDUCE[reduce_type], m, _p(grad_feats), _p(ws), ws.numel(), _stream()),
+        "scatter_backward")
+
+
+# --------------------------------------------------------------------------------------------
+# rulebooks
+# --------------------------------------------------------------------------------------------
+def _triple(v):
+    if isinstance(v, (list, tuple)):
+        if len(v) != 3:
+            raise RuntimeError("expected 3 values, got %r" % (v,))
+        return [int(x) for x in v]
+    return [int(v)] * 3
+
+
+def subm_rulebook(coords, batch, grid_dhw, ksize, rows_sorted=False):
+    """nbr[M, K] i32 for a submanifold conv over coords [M,4] (b,z,y,x)."""
+    _check(coords, "indices", torch.int32)
+    if coords.dim() != 2 or coords.shape[1] != 4:
+        raise RuntimeError("indices must be [M, 4] (b, z, y, x)")
+    m = coords.shape[0]
+    k = _triple(ksize)
+    taps = k[0] * k[1] * k[2]
+    dev = coords.device
+    L = _lib.lib()
+    nbr = torch.empty((m, taps), dtype=torch.int32, device=dev)
+    dhw = _lib.i32x3(grid_dhw)
+    wsb = L.efgb_rulebook_workspace_bytes(int(batch), dhw, m)
+    if wsb == 0:
+        raise RuntimeError("batch*D*H*W = %r does not fit the 32-bit cell id" % ((batch, *grid_dhw),))
+    ws = workspace(wsb, dev)
+    rc = L.efgb_subm_rulebook(_p(coords), m, int(batch), dhw, _lib.i32x3(k), 1 if rows_sorted else 0, _p(nbr), _p(ws),
+                              ws.numel(), _stream())
+    _lib.check(rc, "subm_rulebook")
+    return nbr
+
+
+def conv_out_shape(in_dhw, ksize, stride, padding):
+    return [(int(i) + 2 * p - k) // s + 1 for i, k, s, p in zip(in_dhw, ksize, stride, padding)]
+
+
+def sparse_rulebook(coords, batch, in_dhw, ksize, stride, padding):
+    """Regular sparse conv rulebook. Returns (out_coords[Mo,4], out_dhw, nbr[Mo,K], nbr_t[Mi,K])."""
+    _check(coords, "indices", torch.int32)
+    if coords.dim() != 2 or coords.shape[1] != 4:
+        raise RuntimeError("indices must be [M, 4] (b, z, y, x)")
+    m_in = coords.shape[0]
+    k, s, p = _triple(ksize), _triple(stride), _triple(padding)
+    taps = k[0] * k[1] * k[2]
+    dev = coords.device
+    L = _lib.lib()
+    out_dhw_py = conv_out_shape(in_dhw, k, s, p)
+    if min(out_dhw_py) < 1:
+        raise RuntimeError("sparse conv output shape %r is empty" % (out_dhw_py,))
+    wsb = L.efgb_rulebook_workspace_bytes(int(batch), _lib.i32x3(out_dhw_py), 1)
+    if wsb == 0:
+        raise RuntimeError("batch*D*H*W of the output grid does not fit the 32-bit cell id")
+    ws = workspace(wsb, dev)
+    out_dhw = _lib.i32x3([0, 0, 0])
+    m_dev = torch.zeros((1,), dtype=torch.int32, device=dev)
+    args = (_p(coords), m_in, int(batch), _lib.i32x3(in_dhw), _lib.i32x3(k), _lib.i32x3(s), _lib.i32x3(p))
+    _lib.check(L.efgb_sparse_rulebook_phase1(*args, out_dhw, _p(m_dev), _p(ws), ws.numel(), _stream()),
+               "sparse_rulebook_phase1")
+    m_out = int(m_dev.item())  # the one host sync of a strided conv
+    out_coords = torch.empty((m_out, 4), dtype=torch.int32, device=dev)
+    nbr = torch.empty((m_out, taps), dtype=torch.int32, device=dev)
+    nbr_t = torch.empty((m_in, taps), dtype=torch.int32, device=dev)
+    _lib.check(L.efgb_sparse_rulebook_phase2(*args, m_out, _p(out_coords), _p(nbr), _p(nbr_t), _p(ws), ws.numel(),
+                                             _stream()), "sparse_rulebook_phase2")
+    return out_coords, [int(out_dhw[0]), int(out_dhw[1]), int(out_dhw[2])], nbr, nbr_t
+
+
+# --------------------------------------------------------------------------------------------
+# sparse conv compute
+# --------------------------------------------------------------------------------------------
+def spconv_forward(feats, w_kio, bias, nbr):
+    """out[o] = bias + sum_k feats[nbr[o,k]] @ w_kio[k];  feats [Mi,Cin], w [K,Cin,Cout], nbr [Mo,K]."""
+    _check(feats, "features", torch.float32)
+    _check(w_kio, "weight", torch.float32)
+    _check(nbr, "rulebook", torch.int32)
+    if bias is not None:
+        _check(bias, "bias", torch.float32)
+    taps, c_in, c_out = w_kio.shape
+    if feats.shape[1] != c_in or nbr.shape[1] != taps:
+        raise RuntimeError("spconv_forward: shape mismatch feats %r weight %r rulebook %r" %
+                           (tuple(feats.shape), tuple(w_kio.shape), tuple(nbr.shape)))
+    m_out = nbr.shape[0]
+    out = torch.empty((m_out, c_out), dtype=torch.float32, device=feats.device)
+    L = _lib.lib()
+    rc = L.efgb_spconv_forward(_p(feats), feats.shape[0], c_in, _p(w_kio), _p(bias), _p(nbr), m_out, taps, c_out,
+                               _p(out), _stream())
+    _lib.check(rc, "spconv_forward")
+    return out
+
+
+def spconv_wgrad(feats, grad_out, nbr, taps, c_in, c_out):
+    _check(feats, "features", torch.float32)
+    _check(grad_out, "grad_out", torch.float32)
+    _check(nbr, "rulebook", torch.int32)
+    dw = torch.empty((taps, c_in, c_out), dtype=torch.float32, device=feats.device)
+    L = _lib.lib()
+    rc = L.efgb_spconv_wgrad(_p(feats), feats.shape[0], c_in, _p(grad_out), _p(nbr), nbr.shape[0], taps, c_out, _p(dw),
+                             _stream())
+    _lib.check(rc, "spconv_wgrad")
+    return dw
+
+
+def sparse_to_dense(feats, coords, batch, grid_dhw):
+    _check(feats, "features", torch.float32)
+    _check(coords, "indices", torch.int32)
+    m, c = feats.shape
+    d, h, w = [int(x) for x in grid_dhw]
+    dense = torch.empty((batch, c, d, h, w), dtype=torch.float32, device=feats.device)
+    L = _lib.lib()
+    rc = L.efgb_sparse_to_dense(_p(feats), _p(coords), m, c, int(batch), _lib.i32x3(grid_dhw), _p(dense), _stream())
+    _lib.check(rc, "sparse_to_dense")
+    return dense
+
+
+def dense_to_sparse(dense, coords):
+    _check(dense, "dense", torch.float32)
+    _check(coords, "indices", torch.int32)
+    batch, c, d, h, w = dense.shape
+    m = coords.shape[0]
+    feats = torch.empty((m, c), dtype=torch.float32, device=dense.device)
+    L = _lib.lib()
+    rc = L.efgb_dense_to_sparse(_p(dense), _p(coords), m, c, int(batch), _lib.i32x3([d, h, w]), _p(feats), _stream())
+    _lib.check(rc, "dense_to_sparse")
+    return feats
+
+
+# --------------------------------------------------------------------------------------------
+# box attention
+# --------------------------------------------------------------------------------------------
+def _box_attn_shapes(value, shapes, level_start, loc, attn):
+    _check(value, "value", torch.float32)
+    _check(shapes, "value_spatial_shapes", torch.int64)
+    _check(level_start, "value_level_start_index", torch.int64)
+    _check(loc, "sampling_locations", torch.float32)
+    _check(attn, "attention_weights", torch.float32)
+    if value.dim() != 4 or loc.dim() != 6:
+        raise RuntimeError("box_attn: value must be [B,LV,H,C] and sampling_locations [B,LQ,H,L,P,2]")
+    b, lv, h, ch = value.shape
+    lq, nl, npnt = loc.shape[1], loc.shape[3], loc.shape[4]
+    if loc.shape[0] != b or loc.shape[2] != h or loc.shape[5] != 2 or shapes.shape[0] != nl:
+        raise RuntimeError("box_attn: inconsistent shapes value %r loc %r shapes %r" %
+                           (tuple(value.shape), tuple(loc.shape), tuple(shapes.shape)))
+    if attn.numel() != b * lq * h * nl * npnt:
+        raise RuntimeError("box_attn: attention_weights has %d elements, expected %d" %
+                           (attn.numel(), b * lq * h * nl * npnt))
+    return b, lv, h, ch, nl, lq, npnt
+
+
+def box_attn_forward(value, shapes, level_start, loc, attn):
+    b, lv, h, ch, nl, lq, npnt = _box_attn_shapes(value, shapes, level_start, loc, attn)
+    out = torch.empty((b, lq, h * ch), dtype=torch.float32, device=value.device)
+    L = _lib.lib()
+    rc = L.efgb_box_attn_forward(_p(value), _p(shapes), _p(level_start), _p(loc), _p(attn), b, lv, h, ch, nl, lq, npnt,
+                                 _p(out), _stream())
+    _lib.check(rc, "box_attn_forward")
+    return out
+
+
+def box_attn_backward(value, shapes, level_start, loc, attn, grad_out):
+    b, lv, h, ch, nl, lq, npnt = _box_attn_shapes(value, shapes, level_start, loc, attn)
+    _check(grad_out, "grad_output", torch.float32)
+    grad_value = torch.empty_like(value)
+    grad_loc = torch.empty_like(loc)
+    grad_attn = torch.empty_like(attn)
+    L = _lib.lib()
+    rc = L.efgb_box_attn_backward(_p(value), _p(shapes), _p(level_start), _p(loc), _p(attn), _p(grad_out), b, lv, h, ch,
+                                  nl, lq, npnt, _p(grad_value), _p(grad_loc), _p(grad_attn), _stream())
+    _lib.check(rc, "box_attn_backward")
+    return grad_value, grad_loc, grad_attn

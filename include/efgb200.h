@@ -1,0 +1,187 @@
+/*
+ * efgb200.h — C ABI of the B200-native (sm_100a) 3D-detection hot path that sits
+ * behind EFG's Python operator surface.
+ *
+ * Conventions (every entry point):
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers on the
+ *     caller's current CUDA device unless the parameter is documented as HOST;
+ *   - the caller owns every buffer, including the scratch workspace (size it with
+ *     the matching *_workspace_bytes query); nothing is allocated or freed here;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no entry
+ *     point synchronises the device or touches the legacy default stream;
+ *   - return value: 0 on success, a negative EFGB_E* code on failure;
+ *     efgb_last_error() returns a thread-local description of the last failure.
+ *
+ * Reference interfaces replaced (paths relative to the V2AI/EFG tree):
+ *   efg/operators/src/voxelize/voxelization.h:51-83   hard_voxelize / dynamic_voxelize
+ *   efg/operators/src/voxelize/voxelization.h:96-128  dynamic_point_to_voxel_{forward,backward}
+ *   efg/operators/src/box_attn/box_attn.h:29-83       box_attn_{forward,backward}
+ *   efg/modeling/backbones/sparse_net.py:6-11         spconv.{SubMConv3d,SparseConv3d,SparseConvTensor.dense}
+ *   efg/modeling/readers/voxel_reader.py:14-19        VoxelMeanFeatureExtractor (fused into the voxelizer)
+ */
+#ifndef EFGB200_H_
+#define EFGB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EFGB_OK 0
+#define EFGB_EINVAL (-1)    /* bad argument (null pointer, negative size, unsupported shape) */
+#define EFGB_EWORKSPACE (-2) /* workspace too small */
+#define EFGB_ECUDA (-3)     /* CUDA launch / runtime error */
+#define EFGB_ERANGE (-4)    /* index space does not fit the 32-bit cell id used on device */
+
+typedef void* efgb_stream_t; /* cudaStream_t */
+
+const char* efgb_last_error(void);
+int efgb_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Voxelizer — first-come "hard" voxelization, bit-exact with the reference's CPU twins
+ *   efg/geometry/point_cloud_ops.py:6-53 (numba) and voxelization_cpu.cpp:44-96 (C++):
+ *   c_j = floor((p_j - lo_j) / vs_j) in fp32; points outside the grid are dropped; voxel ids
+ *   are assigned in order of first occurrence; at most max_points points are kept per voxel
+ *   (in input order); the first point that would open voxel number max_voxels+1 ends the
+ *   scene (it and every later point are dropped).  max_voxels < 0 means unlimited.
+ *
+ * A batch of scenes is voxelized in one call: points of scene b are rows
+ * [scene_offsets[b], scene_offsets[b+1]) of `points`; voxels of scene b are emitted compactly
+ * after those of scene b-1.  coors_dim = 3 writes (z,y,x) (reference layout), coors_dim = 4
+ * writes (b,z,y,x) (the layout waymo.py:174-179 `collate` builds).
+ *
+ * Outputs (caller-allocated for cap = sum_b min(max_voxels, points_b) rows, contents of rows
+ * >= the returned count are unspecified):
+ *   voxels   [cap, max_points, F] f32, zero padded   (nullable: skip materialising it)
+ *   coors    [cap, coors_dim] i32
+ *   num_points_per_voxel [cap] i32
+ *   mean_features [cap, F] f32 = sum of kept points / count (voxel_reader.py:14-19; nullable)
+ *   voxel_counts [batch+1] i32: per-scene voxel count, then the total
+ * ------------------------------------------------------------------------------------------ */
+size_t efgb_voxelize_workspace_bytes(int64_t num_points, int batch);
+
+int efgb_hard_voxelize(const float* points, int64_t num_points, int num_features,
+                       const int32_t* scene_offsets, int batch,
+                       const float* voxel_size_host3, const float* coors_range_host6,
+                       int max_points, int max_voxels,
+                       float* voxels, int32_t* coors, int coors_dim,
+                       int32_t* num_points_per_voxel, float* mean_features,
+                       int32_t* voxel_counts,
+                       void* workspace, size_t workspace_bytes, efgb_stream_t stream);
+
+/* dynamic_voxelize (voxelization_cpu.cpp:8-40): per-point (z,y,x), (-1,-1,-1) when dropped. */
+int efgb_dynamic_voxelize(const float* points, int64_t num_points, int num_features,
+                          const float* voxel_size_host3, const float* coors_range_host6,
+                          int32_t* coors, efgb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dynamic scatter (scatter_points_cuda.cu:209-352): reduce point features by integer
+ * coordinate.  Voxels come out in ascending linearised-coordinate order.  Two phases because
+ * the voxel count M is data dependent and the caller owns the outputs:
+ *   phase 1 marks/ranks the occupied cells and writes M to *num_voxels_dev,
+ *   phase 2 fills voxel_feats[M,C], voxel_coors[M,3], point2voxel[N] (-1 = dropped), count[M].
+ * dims_host3 = extent of each coordinate (coors.max(0)+1 in the reference); rows with any
+ * negative coordinate are dropped.  reduce_type: 0 sum, 1 mean, 2 max.
+ * ------------------------------------------------------------------------------------------ */
+size_t efgb_scatter_workspace_bytes(int64_t num_points, const int32_t* dims_host3);
+int efgb_scatter_phase1(const int32_t* coors, int64_t num_points, const int32_t* dims_host3,
+                        int32_t* num_voxels_dev, void* workspace, size_t workspace_bytes,
+                        efgb_stream_t stream);
+int efgb_scatter_phase2(const float* feats, const int32_t* coors, int64_t num_points, int channels,
+                        const int32_t* dims_host3, int reduce_type, int64_t num_voxels,
+                        float* voxel_feats, int32_t* voxel_coors, int32_t* point2voxel,
+                        int32_t* count, void* workspace, size_t workspace_bytes,
+                        efgb_stream_t stream);
+int efgb_scatter_backward(const float* grad_voxel_feats, const float* feats, const float* voxel_feats,
+                          const int32_t* point2voxel, const int32_t* count, int64_t num_points,
+                          int channels, int reduce_type, int64_t num_voxels, float* grad_feats,
+                          void* workspace, size_t workspace_bytes, efgb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Rulebooks, built on device.  Active sites are rows of coords[M,4] i32 = (b,z,y,x) inside a
+ * [batch, D, H, W] grid.  A rulebook is a dense neighbour table nbr[M_out, K] i32 with
+ * K = kd*kh*kw and k = (kz*kh + ky)*kw + kx: nbr[o,k] is the INPUT row that kernel tap k of
+ * output site o reads, or -1.  (The reference delegates this to spconv's indice-pair
+ * generation, sparse_net.py:85-95; the pair list is the set {(k, nbr[o,k], o) : nbr[o,k] >= 0}.)
+ *
+ * Submanifold (SubMConv3d): outputs == inputs (same order); tap k reads coord + k - K/2.
+ * rows_sorted != 0 promises coords are in ascending linear (b,z,y,x) order (true for the
+ * output of efgb_sparse_rulebook_*), which removes one indirection.
+ *
+ * Regular (SparseConv3d): out = floor((in + 2p - k)/s) + 1 per axis; an output site exists
+ * iff at least one input contributes; output rows are emitted in ascending linear order.
+ *   phase 1: mark + rank output cells, write M_out to *num_out_dev;
+ *   phase 2: out_coords[M_out,4], nbr[M_out,K], nbr_t[M_in,K] (nbr_t[j,k] = output row that
+ *            input j feeds through tap k, or -1 — the transposed rulebook used by dgrad).
+ * ------------------------------------------------------------------------------------------ */
+size_t efgb_rulebook_workspace_bytes(int batch, const int32_t* grid_dhw_host3, int64_t num_rows);
+
+int efgb_subm_rulebook(const int32_t* coords, int64_t num_rows, int batch,
+                       const int32_t* grid_dhw_host3, const int32_t* ksize_host3, int rows_sorted,
+                       int32_t* nbr, void* workspace, size_t workspace_bytes, efgb_stream_t stream);
+
+int efgb_sparse_rulebook_phase1(const int32_t* coords_in, int64_t num_in, int batch,
+                                const int32_t* in_dhw_host3, const int32_t* ksize_host3,
+                                const int32_t* stride_host3, const int32_t* padding_host3,
+                                int32_t* out_dhw_host3 /* HOST out */, int32_t* num_out_dev,
+                                void* workspace, size_t workspace_bytes, efgb_stream_t stream);
+
+int efgb_sparse_rulebook_phase2(const int32_t* coords_in, int64_t num_in, int batch,
+                                const int32_t* in_dhw_host3, const int32_t* ksize_host3,
+                                const int32_t* stride_host3, const int32_t* padding_host3,
+                                int64_t num_out, int32_t* out_coords, int32_t* nbr, int32_t* nbr_t,
+                                void* workspace, size_t workspace_bytes, efgb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Sparse convolution as an output-stationary gather-GEMM over a rulebook:
+ *   out[o, :] = bias + sum_k  in[nbr[o,k], :] @ w[k]        (rows with nbr = -1 contribute 0)
+ * w is [K, Cin, Cout] f32 (tap-major; the host mirror permutes spconv's [Cout,kd,kh,kw,Cin]).
+ * dgrad is the same call on (grad_out, w^T per tap, nbr_t); wgrad is below.
+ * fp32 FFMA arithmetic, fp32 accumulation.
+ * ------------------------------------------------------------------------------------------ */
+int efgb_spconv_forward(const float* in_feats, int64_t num_in, int c_in,
+                        const float* w_kio, const float* bias /* nullable [c_out] */,
+                        const int32_t* nbr, int64_t num_out, int num_taps, int c_out,
+                        float* out_feats, efgb_stream_t stream);
+
+/* dw[k, ci, co] = sum_o in[nbr[o,k], ci] * grad_out[o, co]; dw is zero-filled by the callee. */
+int efgb_spconv_wgrad(const float* in_feats, int64_t num_in, int c_in,
+                      const float* grad_out, const int32_t* nbr, int64_t num_out, int num_taps,
+                      int c_out, float* dw_kio, efgb_stream_t stream);
+
+/* SparseConvTensor.dense(): feats[M,C] at coords[M,4] -> out[B,C,D,H,W] (zero filled here);
+ * and its adjoint (gather) for the backward pass. */
+int efgb_sparse_to_dense(const float* feats, const int32_t* coords, int64_t num_rows, int channels,
+                         int batch, const int32_t* grid_dhw_host3, float* dense, efgb_stream_t stream);
+int efgb_dense_to_sparse(const float* dense, const int32_t* coords, int64_t num_rows, int channels,
+                         int batch, const int32_t* grid_dhw_host3, float* feats, efgb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Box attention (box_attn.h:29-83; kernels box_attn_kernel.cuh:275-351 fwd, :35-190 math):
+ *   out[b,q,h,c] = sum_{l,p} attn[b,q,h,l,p] * bilinear(value_l[b,:,h,c], loc[b,q,h,l,p])
+ * with h_im = loc_y*H_l - 0.5, w_im = loc_x*W_l - 0.5, zero padding, taps taken only when
+ * h_im > -1 && w_im > -1 && h_im < H_l && w_im < W_l.
+ *   value [B, LV, H, Ch] f32; spatial_shapes [L,2] i64 (h,w); level_start [L] i64;
+ *   loc [B, LQ, H, L, P, 2] f32 (x,y in [0,1]); attn [B, LQ, H, L, P] f32; out [B, LQ, H*Ch].
+ * backward zero-fills grad_value then accumulates with red.global.add; grad_loc / grad_attn
+ * are written once per element (no atomics).
+ * ------------------------------------------------------------------------------------------ */
+int efgb_box_attn_forward(const float* value, const int64_t* spatial_shapes,
+                          const int64_t* level_start, const float* loc, const float* attn,
+                          int batch, int len_value, int num_heads, int head_dim, int num_levels,
+                          int len_query, int num_points, float* out, efgb_stream_t stream);
+
+int efgb_box_attn_backward(const float* value, const int64_t* spatial_shapes,
+                           const int64_t* level_start, const float* loc, const float* attn,
+                           const float* grad_out, int batch, int len_value, int num_heads,
+                           int head_dim, int num_levels, int len_query, int num_points,
+                           float* grad_value, float* grad_loc, float* grad_attn,
+                           efgb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EFGB200_H_ */

@@ -1,0 +1,47 @@
+"""ORACLE (test infrastructure): build the reference's own C++ CPU voxelizer into oracle/_ref/.
+
+Only possible where /root/reference exists (the build container).  The resulting
+``oracle/_ref/efg_ref_voxelize*.so`` is git-ignored but travels to the GPU box with gpurun, where
+``load()`` imports the prebuilt file.  Sources are compiled where they lie; nothing is copied.
+"""
+import glob
+import importlib.util
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "_ref")
+REF_SRC = "/root/reference/efg/operators/src/voxelize/voxelization_cpu.cpp"
+NAME = "efg_ref_voxelize"
+
+
+def build():
+    if not os.path.exists(REF_SRC):
+        return None
+    existing = glob.glob(os.path.join(OUT, NAME + "*.so"))
+    if existing:
+        return existing[0]
+    os.makedirs(OUT, exist_ok=True)
+    from torch.utils.cpp_extension import load
+
+    load(name=NAME, sources=[os.path.join(HERE, "ref_shim.cpp"), REF_SRC], extra_cflags=["-O2", "-std=c++17"],
+         build_directory=OUT, verbose=False)
+    existing = glob.glob(os.path.join(OUT, NAME + "*.so"))
+    return existing[0] if existing else None
+
+
+def load():
+    """Import the prebuilt reference module, or return None when it was never built."""
+    existing = glob.glob(os.path.join(OUT, NAME + "*.so"))
+    if not existing:
+        return None
+    import torch  # noqa: F401  (libtorch symbols must be loaded first)
+
+    spec = importlib.util.spec_from_file_location(NAME, existing[0])
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+if __name__ == "__main__":
+    print(build())

@@ -1,0 +1,71 @@
+"""CPU: the C-ABI library builds, loads, and exports exactly what include/efgb200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from efg_b200 import _build, _lib
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "efgb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(efgb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_loads():
+    path = _build.build()
+    assert os.path.exists(path)
+    L = _lib.lib()
+    assert L.efgb_version() >= 100
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    _build.build()
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 19
+    for name in declared:
+        assert hasattr(handle, name), "libefgb200.so does not export %s" % name
+        assert name in _lib.SIGNATURES, "efg_b200/_lib.py does not bind %s" % name
+    assert sorted(_lib.SIGNATURES) == declared
+
+
+def test_no_cpu_fallback():
+    """CPU tensors must be rejected loudly by every operator of the path."""
+    import torch
+
+    from efg_b200 import _C
+    from efg_b200.operators import BoxAttnFunction, dynamic_scatter, voxelization
+    from efg_b200.spconv import SparseConvTensor, SubMConv3d
+
+    pts = torch.rand(10, 5)
+    with pytest.raises(RuntimeError):
+        voxelization(pts, [0.1, 0.1, 0.1], [0, 0, 0, 1, 1, 1], 5, 100)
+    with pytest.raises(RuntimeError):
+        voxelization(pts, [0.1, 0.1, 0.1], [0, 0, 0, 1, 1, 1], -1, -1)
+    with pytest.raises(RuntimeError):
+        dynamic_scatter(pts, torch.zeros(10, 3, dtype=torch.int32), "max")
+    with pytest.raises(RuntimeError):
+        _C.box_attn_forward(torch.rand(1, 4, 1, 8), torch.tensor([[2, 2]]), torch.tensor([0]),
+                            torch.rand(1, 3, 1, 1, 2, 2), torch.rand(1, 3, 1, 1, 2), 64)
+    with pytest.raises(RuntimeError):
+        BoxAttnFunction.apply(torch.rand(1, 4, 1, 8), torch.tensor([[2, 2]]), torch.tensor([0]),
+                              torch.rand(1, 3, 1, 1, 2, 2), torch.rand(1, 3, 1, 1, 2), 64)
+    x = SparseConvTensor(torch.rand(4, 3), torch.zeros(4, 4, dtype=torch.int32), [4, 4, 4], 1)
+    with pytest.raises(RuntimeError):
+        SubMConv3d(3, 4, 3, padding=1)(x)
+
+
+def test_product_never_imports_oracle():
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "efg_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M) or "oracle/" in src:
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, "product files reference the oracle: %s" % bad
