@@ -1,0 +1,103 @@
+"""GPU parity: box attention forward/backward vs the golden vectors produced by the reference's
+own torch twin (ms_deform_attn_core_pytorch) and vs the CPU oracle at Voxel-DETR geometry.
+Tolerance 1e-4 absolute on fp32 values of O(1) (north_star: 1e-3)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import box_attn as obox
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+BOX_CASES = sorted(glob.glob(os.path.join(GOLDEN, "box_attn_*.pt")))
+
+
+def _level_start(shapes):
+    return torch.cat([shapes.new_zeros(1), (shapes[:, 0] * shapes[:, 1]).cumsum(0)[:-1]])
+
+
+@pytest.mark.parametrize("path", BOX_CASES, ids=[os.path.basename(p)[9:-3] for p in BOX_CASES])
+def test_box_attn_matches_reference_golden(path):
+    from efg_b200.operators import BoxAttnFunction
+
+    g = torch.load(path)
+    shapes = g["shapes"].cuda()
+    v = g["value"].cuda().requires_grad_(True)
+    l = g["loc"].cuda().requires_grad_(True)
+    a = g["attn"].cuda().requires_grad_(True)
+    out = BoxAttnFunction.apply(v, shapes, _level_start(shapes), l, a, 64)
+    assert torch.allclose(out.detach().cpu(), g["out"], atol=1e-5)
+    out.backward(g["grad_out"].cuda())
+    assert torch.allclose(v.grad.cpu(), g["grad_value"], atol=1e-4)
+    assert torch.allclose(l.grad.cpu(), g["grad_loc"], atol=1e-3, rtol=1e-4)
+    assert torch.allclose(a.grad.cpu(), g["grad_attn"], atol=1e-4)
+
+
+def test_box_attn_voxel_detr_geometry_vs_oracle():
+    """One level 47x47 (quarter of the 188x188 BEV map), 8 heads x 32 ch, 25 points, attention
+    passed as [B,LQ,H,L,5,5] exactly like Box3dAttention does (VD/modules/box_attention.py:108)."""
+    from efg_b200.operators import BoxAttnFunction
+
+    gen = torch.Generator().manual_seed(7)
+    B, H, C, hh, ww, P = 2, 8, 32, 47, 47, 25
+    LQ = hh * ww
+    shapes = torch.tensor([[hh, ww]], dtype=torch.int64)
+    value = torch.randn(B, hh * ww, H, C, generator=gen)
+    ys, xs = torch.meshgrid(torch.linspace(0.5, hh - 0.5, hh) / hh, torch.linspace(0.5, ww - 0.5, ww) / ww,
+                            indexing="ij")
+    centre = torch.stack([xs.reshape(-1), ys.reshape(-1)], -1)[None, :, None, None, None, :]
+    loc = centre + (torch.rand(B, LQ, H, 1, P, 2, generator=gen) - 0.5) * 0.08
+    attn = torch.softmax(torch.randn(B, LQ, H, P, generator=gen), -1).view(B, LQ, H, 1, 5, 5)
+    grad_out = torch.randn(B, LQ, H * C, generator=gen)
+    eo, egv, egl, ega = obox.forward_backward(value, shapes, loc, attn.view(B, LQ, H, 1, P), grad_out)
+    v = value.cuda().requires_grad_(True)
+    l = loc.cuda().requires_grad_(True)
+    a = attn.cuda().requires_grad_(True)
+    out = BoxAttnFunction.apply(v, shapes.cuda(), _level_start(shapes).cuda(), l, a, 64)
+    assert torch.allclose(out.detach().cpu(), eo, atol=1e-5)
+    out.backward(grad_out.cuda())
+    assert torch.allclose(v.grad.cpu(), egv, atol=2e-4)
+    assert torch.allclose(l.grad.cpu(), egl, atol=2e-3, rtol=1e-4)
+    assert torch.allclose(a.grad.cpu().view(B, LQ, H, 1, P), ega, atol=1e-4)
+
+
+def test_box_attn_linearity_in_value_full_size():
+    """Size-independent property at the full 188x188 map: the op is linear in `value` and in `attn`."""
+    from efg_b200 import ops
+
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    B, H, C, hh, ww, P, LQ = 1, 8, 32, 188, 188, 25, 4096
+    shapes = torch.tensor([[hh, ww]], dtype=torch.int64, device="cuda")
+    start = torch.zeros(1, dtype=torch.int64, device="cuda")
+    v1 = torch.randn(B, hh * ww, H, C, device="cuda", generator=gen)
+    v2 = torch.randn(B, hh * ww, H, C, device="cuda", generator=gen)
+    loc = torch.rand(B, LQ, H, 1, P, 2, device="cuda", generator=gen) * 1.1 - 0.05
+    attn = torch.rand(B, LQ, H, 1, P, device="cuda", generator=gen)
+    o1 = ops.box_attn_forward(v1, shapes, start, loc, attn)
+    o2 = ops.box_attn_forward(v2, shapes, start, loc, attn)
+    o12 = ops.box_attn_forward(v1 + 2 * v2, shapes, start, loc, attn)
+    assert torch.allclose(o12, o1 + 2 * o2, atol=1e-4)
+    o3 = ops.box_attn_forward(v1, shapes, start, loc, attn * 3)
+    assert torch.allclose(o3, o1 * 3, atol=1e-4)
+    # all-outside sampling locations give exactly zero and zero gradients
+    far = torch.full_like(loc, 7.0)
+    assert ops.box_attn_forward(v1, shapes, start, far, attn).abs().max().item() == 0.0
+    gv, gl, ga = ops.box_attn_backward(v1, shapes, start, far, attn, torch.ones(B, LQ, H * C, device="cuda"))
+    assert gv.abs().max().item() == 0 and gl.abs().max().item() == 0 and ga.abs().max().item() == 0
+
+
+def test_box_attn_im2col_contract():
+    from efg_b200 import _C
+
+    v = torch.randn(3, 16, 2, 8, device="cuda")
+    shapes = torch.tensor([[4, 4]], device="cuda")
+    start = torch.tensor([0], device="cuda")
+    loc = torch.rand(3, 5, 2, 1, 4, 2, device="cuda")
+    attn = torch.rand(3, 5, 2, 1, 4, device="cuda")
+    with pytest.raises(RuntimeError):
+        _C.box_attn_forward(v, shapes, start, loc, attn, 2)  # 3 % 2 != 0
+    assert _C.box_attn_forward(v, shapes, start, loc, attn, 64).shape == (3, 5, 16)

@@ -1,0 +1,191 @@
+"""GPU parity: device rulebooks (bit-exact vs the CPU oracle) and sparse convolution
+forward / dgrad / wgrad / dense() within 1e-4 of the fp32 oracle (north_star allows 1e-3)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sparse_conv as sc
+from oracle import voxelize as ovox
+
+pytestmark = pytest.mark.gpu
+
+ATOL = 1e-4
+
+
+def _random_sites(rng, batch, dhw, m, sort=False):
+    cells = rng.choice(batch * dhw[0] * dhw[1] * dhw[2], size=m, replace=False)
+    if sort:
+        cells = np.sort(cells)
+    d, h, w = dhw
+    return np.stack([cells // (d * h * w), (cells // (h * w)) % d, (cells // w) % h, cells % w], 1).astype(np.int32)
+
+
+@pytest.mark.parametrize("sort", [False, True])
+@pytest.mark.parametrize("ksize", [3, (3, 1, 1), (1, 3, 3), 5])
+def test_subm_rulebook_exact(sort, ksize):
+    from efg_b200 import ops
+
+    rng = np.random.default_rng(21)
+    batch, dhw = 3, [9, 40, 37]
+    coords = _random_sites(rng, batch, dhw, 4000, sort)
+    nbr = ops.subm_rulebook(torch.from_numpy(coords).cuda(), batch, dhw, ksize, rows_sorted=sort)
+    exp = sc.subm_rulebook(coords, batch, dhw, ksize)
+    assert np.array_equal(nbr.cpu().numpy().astype(np.int64), exp)
+
+
+@pytest.mark.parametrize("geom", [(3, 2, 1), ((3, 1, 1), (2, 1, 1), (1, 0, 0)), (3, 2, (0, 1, 1)),
+                                  ((3, 1, 1), (2, 1, 1), 0), (3, 1, 1), (2, 2, 0)])
+def test_sparse_rulebook_exact(geom):
+    from efg_b200 import ops
+
+    k, s, p = geom
+    rng = np.random.default_rng(22)
+    batch, dhw = 2, [11, 50, 47]
+    coords = _random_sites(rng, batch, dhw, 5000)
+    oc, od, nbr, nbr_t = ops.sparse_rulebook(torch.from_numpy(coords).cuda(), batch, dhw, k, s, p)
+    eoc, eod, enbr, enbr_t = sc.sparse_rulebook(coords, batch, dhw, k, s, p)
+    assert od == eod
+    assert np.array_equal(oc.cpu().numpy(), eoc)
+    assert np.array_equal(nbr.cpu().numpy().astype(np.int64), enbr)
+    assert np.array_equal(nbr_t.cpu().numpy().astype(np.int64), enbr_t)
+    # canonical pair set (order independent definition of rulebook parity)
+    assert np.array_equal(sc.canonical_pairs(nbr.cpu().numpy(), coords, oc.cpu().numpy()),
+                          sc.canonical_pairs(enbr, coords, eoc))
+
+
+def test_rulebooks_full_size_waymo_scene():
+    """Config-1/3 sized: a 150k-point LiDAR-like scene through L0 SubM and the first strided conv."""
+    from efg_b200 import ops
+    from efg_b200.data import WAYMO, make_scene
+
+    pts, _ = make_scene(150000, WAYMO, seed=3)
+    _, c, _ = ovox.hard_voxelize(pts, WAYMO.voxel_size, WAYMO.pc_range, 5, 150000)
+    coords = np.pad(c, ((0, 0), (1, 0))).astype(np.int32)
+    dhw = [41, 1504, 1504]
+    tc = torch.from_numpy(coords).cuda()
+    nbr = ops.subm_rulebook(tc, 1, dhw, 3, rows_sorted=False)
+    assert np.array_equal(nbr.cpu().numpy().astype(np.int64), sc.subm_rulebook(coords, 1, dhw, 3))
+    oc, od, nb, nt = ops.sparse_rulebook(tc, 1, dhw, 3, 2, 1)
+    eoc, eod, enb, ent = sc.sparse_rulebook(coords, 1, dhw, 3, 2, 1)
+    assert od == eod == [21, 752, 752]
+    assert np.array_equal(oc.cpu().numpy(), eoc) and np.array_equal(nb.cpu().numpy().astype(np.int64), enb)
+    assert np.array_equal(nt.cpu().numpy().astype(np.int64), ent)
+    nbr1 = ops.subm_rulebook(oc, 1, od, 3, rows_sorted=True)
+    assert np.array_equal(nbr1.cpu().numpy().astype(np.int64), sc.subm_rulebook(eoc, 1, eod, 3))
+
+
+@pytest.mark.parametrize("cin,cout", [(5, 16), (16, 16), (16, 32), (32, 64), (64, 64), (128, 128), (7, 3), (40, 72)])
+@pytest.mark.parametrize("subm", [True, False])
+def test_conv_forward_backward_vs_oracle(cin, cout, subm):
+    from efg_b200.spconv import SparseConv3d, SparseConvTensor, SubMConv3d
+
+    rng = np.random.default_rng(cin * 100 + cout)
+    torch.manual_seed(cin + cout)
+    batch, dhw = 2, [9, 30, 31]
+    m = 2500
+    coords = _random_sites(rng, batch, dhw, m)
+    feats = torch.randn(m, cin)
+    if subm:
+        mod = SubMConv3d(cin, cout, 3, padding=1, bias=(cin == 5), indice_key="k")
+        nbr = sc.subm_rulebook(coords, batch, dhw, 3)
+    else:
+        mod = SparseConv3d(cin, cout, 3, 2, padding=1, bias=False)
+        _, _, nbr, _ = sc.sparse_rulebook(coords, batch, dhw, 3, 2, 1)
+    w = mod.weight.detach().clone().requires_grad_(True)
+    b = mod.bias.detach().clone().requires_grad_(True) if mod.bias is not None else None
+    fo = feats.clone().requires_grad_(True)
+    yo = sc.conv(fo, w, b, nbr)
+    go = torch.randn_like(yo)
+    yo.backward(go)
+
+    mod = mod.cuda()
+    fg = feats.cuda().requires_grad_(True)
+    x = SparseConvTensor(fg, torch.from_numpy(coords).cuda(), dhw, batch)
+    y = mod(x)
+    assert torch.allclose(y.features.detach().cpu(), yo.detach(), atol=ATOL)
+    y.features.backward(go.cuda())
+    assert torch.allclose(fg.grad.cpu(), fo.grad, atol=ATOL)
+    scale = max(1.0, float(w.grad.abs().max()))
+    assert torch.allclose(mod.weight.grad.cpu(), w.grad, atol=ATOL * scale, rtol=1e-4)
+    if b is not None:
+        assert torch.allclose(mod.bias.grad.cpu(), b.grad, atol=ATOL * scale, rtol=1e-4)
+
+
+def test_config1_subm16_on_20k_cloud():
+    """BASELINE.json configs[0]: 20k-pt cloud -> voxelize -> one SubMConv3d(16->16, 3^3), bs=1."""
+    from efg_b200 import ops
+    from efg_b200.data import WAYMO, make_scene
+    from efg_b200.spconv import SparseConvTensor, SubMConv3d
+
+    pts, _ = make_scene(20000, WAYMO, seed=0)
+    ov, oc, on = ovox.hard_voxelize(pts, WAYMO.voxel_size, WAYMO.pc_range, 5, 150000)
+    r = ops.hard_voxelize_batched(torch.from_numpy(pts).cuda(), torch.tensor([0, 20000], dtype=torch.int32).cuda(),
+                                  WAYMO.voxel_size, WAYMO.pc_range, 5, 150000, coors_dim=4)
+    m = int(r["counts"][-1].item())
+    coords = r["coors"][:m]
+    assert np.array_equal(coords[:, 1:].cpu().numpy(), oc)
+    g = torch.Generator().manual_seed(0)
+    feats = torch.randn(m, 16, generator=g)
+    conv = SubMConv3d(16, 16, 3, padding=1, bias=False)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=torch.Generator().manual_seed(1)) * 0.05)
+    nbr = sc.subm_rulebook(np.pad(oc, ((0, 0), (1, 0))), 1, [41, 1504, 1504], 3)
+    exp = sc.conv(feats, conv.weight.detach(), None, nbr)
+    y = conv.cuda()(SparseConvTensor(feats.cuda(), coords, [41, 1504, 1504], 1))
+    assert (y.features.cpu() - exp).abs().max().item() < 1e-5
+
+
+def test_dense_roundtrip_and_grad():
+    from efg_b200.spconv import SparseConvTensor
+
+    rng = np.random.default_rng(5)
+    batch, dhw = 2, [3, 20, 23]
+    coords = _random_sites(rng, batch, dhw, 700, sort=True)
+    feats = torch.randn(700, 48)
+    fg = feats.cuda().requires_grad_(True)
+    dense = SparseConvTensor(fg, torch.from_numpy(coords).cuda(), dhw, batch).dense()
+    exp = sc.to_dense(feats, coords, batch, dhw)
+    assert torch.equal(dense.cpu(), exp)
+    g = torch.randn_like(exp)
+    dense.backward(g.cuda())
+    c = torch.from_numpy(coords).long()
+    assert torch.equal(fg.grad.cpu(), g[c[:, 0], :, c[:, 1], c[:, 2], c[:, 3]])
+
+
+def test_sequential_block_vs_cpu_oracle_modules():
+    """A residual block wired like sparse_net.py:120-165 on both implementations, same weights."""
+    from torch import nn
+
+    import efg_b200.spconv as gsp
+    from oracle import spconv_cpu as csp
+
+    def block(sp):
+        torch.manual_seed(0)
+        conv = sp.SparseSequential(sp.SparseConv3d(8, 16, 3, 2, padding=1, bias=False), nn.BatchNorm1d(16), nn.ReLU(),
+                                   sp.SubMConv3d(16, 16, 3, padding=1, bias=False, indice_key="r"), nn.BatchNorm1d(16))
+        short = sp.SparseSequential(sp.SparseConv3d(8, 16, 3, 2, padding=1, bias=False), nn.BatchNorm1d(16))
+        return nn.ModuleList([conv, short])
+
+    rng = np.random.default_rng(9)
+    batch, dhw = 2, [9, 26, 25]
+    coords = _random_sites(rng, batch, dhw, 3000)
+    feats = torch.randn(3000, 8)
+    cb, gb = block(csp), block(gsp)
+    gb.load_state_dict(cb.state_dict())
+    gb = gb.cuda()
+    xc = csp.SparseConvTensor(feats.clone().requires_grad_(True), torch.from_numpy(coords), dhw, batch)
+    xg = gsp.SparseConvTensor(feats.cuda().requires_grad_(True), torch.from_numpy(coords).cuda(), dhw, batch)
+    oc = cb[0](xc)
+    yc = torch.relu(oc.features + cb[1](xc).features)
+    og = gb[0](xg)
+    yg = torch.relu(og.features + gb[1](xg).features)
+    assert np.array_equal(og.indices.cpu().numpy(), oc.indices.numpy())
+    assert torch.allclose(yg.detach().cpu(), yc.detach(), atol=1e-4)
+    dc = oc.replace_feature(yc).dense()
+    dg = og.replace_feature(yg).dense()
+    assert torch.allclose(dg.detach().cpu(), dc.detach(), atol=1e-4)
+    dc.square().sum().backward()
+    dg.square().sum().backward()
+    for (n1, p1), (n2, p2) in zip(cb.named_parameters(), gb.named_parameters()):
+        scale = max(1.0, float(p1.grad.abs().max()))
+        assert torch.allclose(p2.grad.cpu(), p1.grad, atol=2e-4 * scale, rtol=1e-3), n1
