@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — scenes/s of one Voxel-DETR training step on synthetic Waymo-shaped scenes.
+
+    python bench.py --gpus N --steps K --warmup W            # the B200 path (efg_b200, CUDA kernels)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): Voxel-DETR 1-frame,
+300 queries, 2 scenes of 150k points per GPU, Waymo grid 1504x1504x40; one step = GPU voxelization
+(+fused mean-VFE) -> sparse ResNet18 -> FPN(p3) -> 3 box-attention encoder layers -> top-k proposals
+-> 3 decoder layers -> heads -> Hungarian matching -> losses -> backward -> gradient all-reduce ->
+AdamW update.  fp32 throughout (the reference runs fp32, SURVEY.md §5 AMP row).
+
+JSON line keys (see the task contract): value = scenes/s with the point clouds already in HBM;
+e2e = the same step through the public model API from pinned HOST buffers (H2D of the points and
+D2H of the loss inside the timed region); roofline = the dominant efg_b200 kernel family measured
+with CUDA events in-situ; cpu_baseline = the oracle-backed model on the host cores on a bounded
+sample (one scene).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+POINTS_PER_SCENE = 150000
+SCENES_PER_GPU = 2
+NUM_QUERIES = 300
+WORKLOAD = "voxel_detr_waymo_1f_q300_bs2_150kpts"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="efgb200", choices=["efgb200", "reference"])
+    ap.add_argument("--points", type=int, default=POINTS_PER_SCENE)
+    ap.add_argument("--scenes", type=int, default=SCENES_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-points", type=int, default=POINTS_PER_SCENE)
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_scenes(n_scenes, n_points, seed):
+    from efg_b200.data import WAYMO, make_scene
+
+    return [make_scene(n_points, WAYMO, seed=seed * 100 + i) for i in range(n_scenes)]
+
+
+# -------------------------------------------------------------------------------------------------
+# B200 arm
+# -------------------------------------------------------------------------------------------------
+def run_efgb200(args):
+    import torch.distributed as dist
+
+    from efg_b200 import _lib, ops
+    from efg_b200.config import voxel_detr_config
+    from efg_b200.detectors.voxel_detr import VoxelDETR
+    from efg_b200.parallel import GradAverager, init_distributed
+
+    rank, local_rank, world = init_distributed()
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    torch.manual_seed(0)
+
+    cfg = voxel_detr_config(model={"device": "cuda:%d" % local_rank, "transformer": {"num_queries": NUM_QUERIES}})
+    model = VoxelDETR(cfg).train()
+    averager = GradAverager(model)
+    averager.broadcast_parameters()
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=0.01,
+                            betas=(0.9, 0.99), eps=1e-9)
+
+    # a few distinct batches so consecutive steps do not see identical data
+    n_batches = 2
+    host_batches = [make_scenes(args.scenes, args.points, seed=1 + rank * 10 + b) for b in range(n_batches)]
+    pinned = [[(torch.from_numpy(p).pin_memory(), a) for p, a in hb] for hb in host_batches]
+    resident = [[(t.to(dev), a) for t, a in pb] for pb in pinned]
+    h2d_bytes = sum(t.numel() * 4 for t, _ in pinned[0])
+    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step(batch):
+        opt.zero_grad(set_to_none=True)
+        losses = model([({"points": p}, {"annotations": a}) for p, a in batch])
+        total = sum(v for k, v in losses.items() if k.startswith("loss"))
+        total.backward()
+        averager.average_gradients()
+        opt.step()
+        return total
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(batches, steps, from_host):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ms = 0.0
+        last = None
+        for i in range(steps):
+            l2_flush.zero_()  # flush L2 between timed iterations (outside the timed span)
+            b = batches[i % len(batches)]
+            barrier()
+            ev0.record()
+            if from_host:
+                b = [(t.to(dev, non_blocking=True), a) for t, a in b]
+            total = step(b)
+            if from_host:
+                last = float(total.item())  # D2H read of the step's result
+            ev1.record()
+            torch.cuda.synchronize()
+            ms += ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, last
+
+    for i in range(max(args.warmup, 3)):
+        step(resident[i % n_batches])
+    barrier()
+
+    launches0 = _lib.lib().efgb_launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev, _ = timed(resident, args.steps, from_host=False)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _lib.lib().efgb_launch_count() - launches0
+    ms_e2e, last_loss = timed(pinned, args.steps, from_host=True)
+
+    scenes_total = args.scenes * world * args.steps
+    value = scenes_total / (ms_dev / 1e3)
+    e2e_value = scenes_total / (ms_e2e / 1e3)
+
+    # in-situ kernel attribution (extra steps, CUDA events around each library launch)
+    ops.PROFILER = ops.KernelProfiler()
+    prof_steps = 2
+    t_prof0 = torch.cuda.Event(enable_timing=True)
+    t_prof1 = torch.cuda.Event(enable_timing=True)
+    t_prof0.record()
+    for i in range(prof_steps):
+        step(resident[i % n_batches])
+    t_prof1.record()
+    summary = ops.PROFILER.summary()
+    ops.PROFILER = None
+    prof_ms = t_prof0.elapsed_time(t_prof1) / prof_steps
+
+    if rank != 0:
+        return
+    peaks = measured_peaks()
+    kernels = {}
+    for fam, d in summary.items():
+        ms_per_launch = d["ms"] / d["launches"]
+        kernels[fam] = {"launches_per_step": d["launches"] / prof_steps, "ms_per_step": round(d["ms"] / prof_steps, 4),
+                        "gbs": round(d["bytes"] / d["launches"] / (ms_per_launch * 1e-3) / 1e9, 1),
+                        "tflops": round(d["flops"] / d["launches"] / (ms_per_launch * 1e-3) / 1e12, 2)}
+    dom = max(summary.items(), key=lambda kv: kv[1]["ms"])
+    dfam, dd = dom
+    d_ms = dd["ms"] / dd["launches"]
+    achieved = dd["bytes"] / dd["launches"] / (d_ms * 1e-3) / 1e9
+    roofline = {"kernel": dfam, "bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": None, "peak_source": peaks["source"],
+                "avg_launch_ms": round(d_ms, 4), "share_of_step": round(dd["ms"] / prof_steps / prof_ms, 4)}
+
+    out = {
+        "metric": "scenes/sec Voxel-DETR fwd+bwd", "value": round(value, 3), "unit": "scenes/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_dev / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "scenes_per_gpu": args.scenes, "points_per_scene": args.points,
+                   "num_queries": NUM_QUERIES, "grid": "1504x1504x40", "step": "voxelize+fwd+bwd+allreduce+adamw",
+                   "parallelism": "dp%d" % world, "l2": "flushed between timed iterations (256 MiB memset)"},
+        "e2e": {"value": round(e2e_value, 3), "unit": "scenes/s", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": last_loss},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernels": kernels,
+        "profiled_step_ms": round(prof_ms, 3),
+    }
+    if not args.no_cpu_baseline and world >= 1:
+        out["cpu_baseline"] = cpu_baseline(args, steps=1)
+    print(json.dumps(out), flush=True)
+
+
+# -------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle restatement; spconv itself is not installable here)
+# -------------------------------------------------------------------------------------------------
+def cpu_step_fn(n_points, seed=1):
+    from efg_b200.config import voxel_detr_config
+    from efg_b200.detectors.voxel_detr import VoxelDETR
+    from oracle.backend_cpu import cpu_backend, voxelized_sample
+
+    torch.manual_seed(0)
+    cfg = voxel_detr_config(model={"device": "cpu", "transformer": {"num_queries": NUM_QUERIES}})
+    model = VoxelDETR(cfg, backend=cpu_backend(), prune_unused=False).train()  # the reference evaluates every FPN level
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, betas=(0.9, 0.99), eps=1e-9)
+    scenes = make_scenes(1, n_points, seed=seed)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        # the reference voxelizes on the host (numba loop == oracle C loop), then collates
+        batch = [(voxelized_sample(p, cfg.dataset), {"annotations": a}) for p, a in scenes]
+        losses = model(batch)
+        total = sum(v for k, v in losses.items() if k.startswith("loss"))
+        total.backward()
+        opt.step()
+        return float(total)
+
+    return step
+
+
+def cpu_baseline(args, steps=1):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_step_fn(args.cpu_points)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return {"value": round(steps / dt, 5), "unit": "scenes/s", "cores": cores, "kind": "port",
+            "sample": "%d step(s) of ONE scene (%d pts, full 1504x1504x40 grid, 300 queries), oracle CPU backend, "
+                      "torch threads=%d, %.1f s" % (steps, args.cpu_points, cores, dt)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_step_fn(args.cpu_points)
+    warm = min(args.warmup, 1)
+    for _ in range(warm):
+        step()
+    steps = max(1, min(args.steps, 3))  # bounded: each step is tens of seconds of host work
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = steps / dt
+    out = {
+        "impl": "reference", "metric": "scenes/sec Voxel-DETR fwd+bwd", "value": round(value, 5), "unit": "scenes/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": round(dt / steps * 1e3, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "scenes_per_step": 1, "points_per_scene": args.cpu_points,
+                   "num_queries": NUM_QUERIES, "grid": "1504x1504x40", "step": "voxelize+fwd+bwd+adamw",
+                   "note": "reference algorithm on host CPU: oracle restatement (spconv is not installable here); "
+                           "each step is a bounded sample of one scene"},
+        "cpu_baseline": {"value": round(value, 5), "unit": "scenes/s", "cores": cores, "kind": "port",
+                         "sample": "%d step(s) x 1 scene, %.1f s" % (steps, dt)},
+        "e2e": {"value": round(value, 5), "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_efgb200(a)

@@ -21,6 +21,7 @@ _host_f32 = ctypes.POINTER(ctypes.c_float)
 SIGNATURES = {
     "efgb_last_error": (ctypes.c_char_p, []),
     "efgb_version": (_int, []),
+    "efgb_launch_count": (ctypes.c_uint64, []),
     "efgb_voxelize_workspace_bytes": (_sz, [_i64, _int]),
     "efgb_hard_voxelize": (_int, [_vp, _i64, _int, _vp, _int, _host_f32, _host_f32, _int, _int,
                                   _vp, _vp, _int, _vp, _vp, _vp, _vp, _sz, _vp]),

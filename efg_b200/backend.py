@@ -13,6 +13,9 @@ class Backend:
         self.spconv = spconv  # namespace with SparseConvTensor, SparseSequential, SubMConv3d, SparseConv3d, SparseModule
         self.box_attn = box_attn  # callable(value, shapes, level_start, loc, attn, im2col_step) -> [B, LQ, H*C]
 
+    def __deepcopy__(self, memo):  # shared by module clones (get_clones deep-copies layers)
+        return self
+
 
 _cuda = None
 

@@ -6,6 +6,7 @@
 namespace efgb {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launch_count = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -160,3 +161,4 @@ int cells_scan(CellWord* cells, int64_t num_words, uint32_t* total_dev, uint32_t
 
 extern "C" const char* efgb_last_error(void) { return efgb::g_err; }
 extern "C" int efgb_version(void) { return 100; }
+extern "C" uint64_t efgb_launch_count(void) { return efgb::g_launch_count; }

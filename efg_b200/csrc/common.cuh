@@ -32,8 +32,11 @@ void set_error(const char* fmt, ...);
     }                                                                                   \
   } while (0)
 
+extern unsigned long long g_launch_count;  // kernels launched by this library (bench.py reports it)
+
 #define EFGB_LAUNCH_OK(name)                                                                  \
   do {                                                                                        \
+    ++::efgb::g_launch_count;                                                                 \
     cudaError_t _e = cudaGetLastError();                                                      \
     if (_e != cudaSuccess) {                                                                  \
       ::efgb::set_error("launch of %s failed: %s (%s:%d)", name, cudaGetErrorString(_e),      \

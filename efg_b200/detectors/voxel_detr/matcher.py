@@ -1,0 +1,59 @@
+"""Hungarian matching between predictions and ground truth (VD/modules/matcher.py:9-91).
+
+cost = w_bbox * L1(box6) + w_class * focal-cost + w_giou * (-GIoU3D axis-aligned) + w_rad * L1(heading)
+The cost matrices of all scenes are built on the GPU, moved to the host in ONE transfer, and
+solved with scipy's ``linear_sum_assignment`` exactly like the reference."""
+import torch
+from scipy.optimize import linear_sum_assignment
+from torch import nn
+
+from .box_utils import cxcyczlwh_to_corners, generalized_box3d_iou
+
+
+class HungarianMatcher3d(nn.Module):
+    def __init__(self, cost_class=1.0, cost_bbox=1.0, cost_giou=1.0, cost_rad=1.0):
+        super().__init__()
+        self.cost_class, self.cost_bbox, self.cost_giou, self.cost_rad = cost_class, cost_bbox, cost_giou, cost_rad
+        assert cost_class != 0 or cost_bbox != 0 or cost_giou != 0 or cost_rad != 0, "all costs cant be 0"
+
+    @torch.no_grad()
+    def cost_matrices(self, outputs, targets):
+        logits, boxes = outputs["pred_logits"], outputs["pred_boxes"]
+        if "topk_indexes" in outputs:
+            idx = outputs["topk_indexes"]
+            logits = torch.gather(logits, 1, idx.expand(-1, -1, logits.shape[-1]))
+            boxes = torch.gather(boxes, 1, idx.expand(-1, -1, boxes.shape[-1]))
+        prob = logits.float().sigmoid()
+        alpha, gamma = 0.25, 2.0
+        neg = (1 - alpha) * (prob ** gamma) * (-(1 - prob + 1e-8).log())
+        pos = alpha * ((1 - prob) ** gamma) * (-(prob + 1e-8).log())
+        cls_cost = pos - neg
+        mats = []
+        for i, tgt in enumerate(targets):
+            tb = tgt["gt_boxes"].float()
+            box6, rad = boxes[i, :, :6].float(), boxes[i, :, 6:].float()
+            c = self.cost_bbox * torch.cdist(box6, tb[:, :6], p=1)
+            c = c + self.cost_class * cls_cost[i][:, tgt["labels"]]
+            c = c - self.cost_giou * generalized_box3d_iou(cxcyczlwh_to_corners(box6), cxcyczlwh_to_corners(tb[:, :6]))
+            c = c + self.cost_rad * torch.cdist(rad, tb[:, 6:], p=1)
+            mats.append(c)
+        return mats
+
+    @torch.no_grad()
+    def forward(self, outputs, targets):
+        mats = self.cost_matrices(outputs, targets)
+        return self.solve(mats)
+
+    @staticmethod
+    def solve(mats):
+        if not mats:
+            return []
+        q = mats[0].shape[0]
+        sizes = [m.shape[1] for m in mats]
+        host = torch.cat(mats, dim=1).cpu() if sum(sizes) else torch.zeros((q, 0))
+        out, off = [], 0
+        for n in sizes:
+            i, j = linear_sum_assignment(host[:, off:off + n].numpy())
+            out.append((torch.as_tensor(i, dtype=torch.int64), torch.as_tensor(j, dtype=torch.int64)))
+            off += n
+        return out

@@ -1,0 +1,189 @@
+"""Voxel-DETR (VD/voxel_detr.py:15-206): mean-VFE reader -> SparseResNet18 + FPN (p3) -> 1x1 conv +
+GroupNorm -> box-attention encoder -> top-k proposals -> decoder -> per-layer detection heads;
+training returns the loss dict, evaluation the decoded top-300 boxes per scene.
+
+``model(batched_inputs)`` takes the reference's list of ``(point_voxels, info)`` pairs.  Two input
+forms are accepted for ``point_voxels``:
+  * the reference's CPU-voxelized dict (``voxels``, ``coordinates``, ``num_points_per_voxel``, ``shape``) —
+    collated and copied to the device like efg/data/datasets/waymo/waymo.py:143-183;
+  * a dict with only ``points`` (numpy [N,F] or a device tensor): the scene is voxelized on the GPU
+    by the fused hash voxelizer + mean-VFE (bit-identical voxels, no CPU pass).
+"""
+import copy
+
+import numpy as np
+import torch
+from torch import nn
+
+from ... import ops
+from ...backend import cuda_backend
+from ...modeling.fpn import build_resnet_fpn_backbone
+from ...modeling.voxel_reader import VoxelMeanFeatureExtractor
+from .box_coder import VoxelBoxCoder3D
+from .heads import Det3DHead
+from .position_encoding import build_position_encoding
+from .transformer import Transformer
+
+
+class Backbone3d(nn.Module):
+    def __init__(self, hidden_dim, reader, extractor, position_encoding, out_features=()):
+        super().__init__()
+        self.reader = reader
+        self.extractor = extractor
+        self.position_encoding = build_position_encoding(position_encoding, hidden_dim)
+        self.out_features = list(out_features)
+        self.num_channels = [extractor.out_channels] * len(self.out_features)
+
+    def forward(self, voxels, coordinates, num_points_per_voxel, batch_size, input_shape):
+        encoded = self.reader(voxels, num_points_per_voxel, coordinates)
+        feats = self.extractor(encoded, coordinates, batch_size, input_shape)
+        return [(feats[f], self.position_encoding(feats[f]).type_as(feats[f])) for f in self.out_features]
+
+
+def collate_voxels(samples, device):
+    """The voxel part of waymo.py:143-183: concatenate per-scene arrays, prepend the batch index."""
+    voxels = torch.from_numpy(np.concatenate([s["voxels"] for s in samples], 0)).to(device)
+    npv = torch.from_numpy(np.concatenate([s["num_points_per_voxel"] for s in samples], 0)).to(device)
+    coords = np.concatenate([np.pad(s["coordinates"], ((0, 0), (1, 0)), mode="constant", constant_values=i)
+                             for i, s in enumerate(samples)], 0)
+    return voxels, torch.from_numpy(coords).to(device), npv, np.asarray(samples[0]["shape"])
+
+
+class VoxelDETR(nn.Module):
+    def __init__(self, config, backend=None, prune_unused=True):
+        super().__init__()
+        self.backend = [backend or cuda_backend()]
+        self.device = torch.device(config.model.device)
+        self.hidden_dim = config.model.hidden_dim
+        self.aux_loss = config.model.aux_loss
+        self.num_classes = len(config.dataset.classes)
+        self.num_queries = config.model.transformer.num_queries
+        self.config = config
+
+        input_dim = len(config.dataset.format) if config.dataset.nsweeps == 1 else len(config.dataset.format) + 1
+        self.input_dim = input_dim
+        reader = VoxelMeanFeatureExtractor(**config.model.backbone.reader, num_input_features=input_dim)
+        extractor = build_resnet_fpn_backbone(config.model.backbone.extractor, input_dim, backend=self.backend[0])
+        if prune_unused:
+            extractor.set_needed(config.model.backbone.out_features)
+        self.backbone = Backbone3d(config.model.backbone.hidden_dim, reader, extractor,
+                                   config.model.backbone.position_encoding,
+                                   out_features=config.model.backbone.out_features)
+        self.input_proj = nn.ModuleList([
+            nn.Sequential(nn.Conv2d(c, self.hidden_dim, kernel_size=1), nn.GroupNorm(32, self.hidden_dim))
+            for c in self.backbone.num_channels])
+        for m in self.input_proj.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.xavier_uniform_(m.weight, gain=1)
+                nn.init.constant_(m.bias, 0)
+
+        t = config.model.transformer
+        self.transformer = self._build_transformer(config, t)
+        self.transformer.proposal_head = Det3DHead(config, with_aux=False, with_metrics=False, num_classes=1,
+                                                   num_layers=1)
+        self.transformer.decoder.detection_head = Det3DHead(config, with_aux=True, with_metrics=True,
+                                                            num_classes=self.num_classes, num_layers=t.dec_layers)
+        self.box_coder = VoxelBoxCoder3D(config.dataset.voxel_size, config.dataset.pc_range, device=self.device)
+        grid = np.round((np.asarray(config.dataset.pc_range[3:], dtype=np.float32) -
+                         np.asarray(config.dataset.pc_range[:3], dtype=np.float32)) /
+                        np.asarray(config.dataset.voxel_size, dtype=np.float32)).astype(np.int64)
+        self.grid_size = grid  # (x, y, z)
+        self.to(self.device)
+
+    def _build_transformer(self, config, t):
+        return Transformer(d_model=t.hidden_dim, nhead=t.nhead, nlevel=len(config.model.backbone.out_features),
+                           num_encoder_layers=t.enc_layers, num_decoder_layers=t.dec_layers,
+                           dim_feedforward=t.dim_feedforward, dropout=t.dropout, num_queries=t.num_queries,
+                           backend=self.backend[0])
+
+    # ---------------------------------------------------------------------------------------
+    def voxelize_on_device(self, samples):
+        """GPU path: samples hold raw ``points``; one fused voxelize + mean-VFE launch sequence for the batch."""
+        ds = self.config.dataset
+        pts, sizes = [], []
+        for s in samples:
+            p = s["points"]
+            if not isinstance(p, torch.Tensor):
+                p = torch.from_numpy(np.ascontiguousarray(p, dtype=np.float32))
+            pts.append(p.to(self.device, non_blocking=True))
+            sizes.append(p.shape[0])
+        points = torch.cat(pts, 0) if len(pts) > 1 else pts[0]
+        offs = torch.tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int32).to(self.device,
+                                                                                           non_blocking=True)
+        max_voxels = ds.get("max_voxel_num", 150000)
+        if isinstance(max_voxels, (list, tuple)):
+            max_voxels = max_voxels[0] if self.training else max_voxels[1]
+        r = ops.hard_voxelize_batched(points.contiguous(), offs, ds.voxel_size, ds.pc_range,
+                                      ds.get("max_points_in_voxel", 5), max_voxels, coors_dim=4, want_voxels=False,
+                                      want_mean=True)
+        m = int(r["counts"][-1].item())  # one host sync: the voxel count sizes every later tensor
+        return r["mean"][:m], r["coors"][:m], r["num_points_per_voxel"][:m], self.grid_size
+
+    def encode_targets(self, batched_inputs):
+        targets = []
+        for _, info in batched_inputs:
+            ann = info["annotations"]
+            t = {k: torch.as_tensor(np.asarray(ann[k]), device=self.device)
+                 for k in ("gt_boxes", "difficulty", "num_points_in_gt", "labels") if k in ann}
+            targets.append(self.box_coder.encode(t))
+        return targets
+
+    def extract(self, batched_inputs):
+        batch_size = len(batched_inputs)
+        samples = [bi[0] for bi in batched_inputs]
+        if "voxels" in samples[0]:
+            voxels, coords, npv, input_shape = collate_voxels(samples, self.device)
+        else:
+            voxels, coords, npv, input_shape = self.voxelize_on_device(samples)
+        feats_pos = self.backbone(voxels, coords, npv, batch_size, input_shape)
+        features = [self.input_proj[i](fp[0]) for i, fp in enumerate(feats_pos)]
+        return features, [fp[1] for fp in feats_pos]
+
+    def forward(self, batched_inputs):
+        targets = self.encode_targets(batched_inputs) if self.training else None
+        features, pos = self.extract(batched_inputs)
+        hs, init_ref, inter_refs, memory, anchors, topk_idx = self.transformer(features, pos)
+
+        head = self.transformer.decoder.detection_head
+        cls_out, box_out = [], []
+        for i in range(hs.shape[0]):
+            ref = init_ref if i == 0 else inter_refs[i - 1]
+            c, b = head(hs[i], ref, i)
+            cls_out.append(c)
+            box_out.append(b)
+        cls_out, box_out = torch.stack(cls_out), torch.stack(box_out)
+
+        if self.training:
+            return self.losses(cls_out, box_out, memory, anchors, topk_idx, targets)
+        return self.postprocess(cls_out[-1], box_out[-1])
+
+    def losses(self, cls_out, box_out, memory, anchors, topk_idx, targets):
+        losses = {}
+        prop = self.transformer.proposal_head
+        num_boxes = prop.losses.normaliser(targets, cls_out.device)
+        enc_cls, enc_box = prop(memory, anchors)
+        bin_targets = [dict(t, labels=torch.zeros_like(t["labels"])) for t in targets]
+        enc = prop.compute_losses({"topk_indexes": topk_idx, "pred_logits": enc_cls, "pred_boxes": enc_box},
+                                  bin_targets, num_boxes)
+        losses.update({k + "_enc": v for k, v in enc.items()})
+        outputs = {"pred_logits": cls_out[-1], "pred_boxes": box_out[-1],
+                   "aux_outputs": [{"pred_logits": a, "pred_boxes": b} for a, b in zip(cls_out[:-1], box_out[:-1])]}
+        losses.update(self.transformer.decoder.detection_head.compute_losses(outputs, targets, num_boxes))
+        return losses
+
+    def postprocess(self, logits, boxes):
+        """sigmoid -> top-300 over (query, class) -> decode (VD/voxel_detr.py:168-198)."""
+        prob = logits.sigmoid().view(logits.shape[0], -1)
+        boxes = self.box_coder.decode(boxes)
+        k = min(300, prob.shape[1])
+        scores, idx = torch.topk(prob, k, dim=1, sorted=False)
+        q = idx.div(logits.shape[2], rounding_mode="floor")
+        labels = idx % logits.shape[2] + 1
+        picked = torch.gather(boxes, 1, q.unsqueeze(-1).repeat(1, 1, boxes.shape[-1]))
+        return [{"scores": s.detach().cpu(), "labels": l.detach().cpu(), "boxes3d": b.detach().cpu()}
+                for s, l, b in zip(scores, labels, picked)]
+
+
+def build_model(self, config, backend=None):
+    """Plugin entry point, same signature as the playground's ``net.build_model(self, config)``."""
+    return VoxelDETR(config, backend=backend)

@@ -1,0 +1,181 @@
+"""Voxel-DETR transformer (VD/transformer.py:9-238): a box-attention encoder over the flattened
+BEV map, top-k proposal selection from a 1-class head on the encoder output, and a decoder of
+(dense self-attention over the queries -> box cross-attention into the BEV memory -> FFN) layers
+with iterative reference-window refinement."""
+import copy
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .box_attention import Box3dAttention
+
+
+class MLP(nn.Module):
+    def __init__(self, input_dim, hidden_dim, output_dim, num_layers):
+        super().__init__()
+        self.num_layers = num_layers
+        dims = [input_dim] + [hidden_dim] * (num_layers - 1) + [output_dim]
+        self.layers = nn.ModuleList(nn.Linear(a, b) for a, b in zip(dims[:-1], dims[1:]))
+
+    def forward(self, x):
+        for i, layer in enumerate(self.layers):
+            x = layer(x)
+            if i < self.num_layers - 1:
+                x = F.relu(x)
+        return x
+
+
+def get_clones(module, n):
+    return nn.ModuleList([copy.deepcopy(module) for _ in range(n)])
+
+
+def _act(name):
+    return {"relu": F.relu, "gelu": F.gelu, "glu": F.glu}[name]
+
+
+def _add_pos(t, pos):
+    return t if pos is None else t + pos
+
+
+class TransformerEncoderLayer(nn.Module):
+    def __init__(self, d_model, nhead, nlevel, dim_feedforward, dropout, activation, backend=None):
+        super().__init__()
+        self.self_attn = Box3dAttention(d_model, nlevel, nhead, with_rotation=False, backend=backend)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.dropout = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.dropout1 = nn.Dropout(dropout)
+        self.dropout2 = nn.Dropout(dropout)
+        self.activation = _act(activation)
+
+    def forward(self, src, pos, src_shape, src_start_idx, ref_windows):
+        attended = self.self_attn(_add_pos(src, pos), src, src_shape, None, src_start_idx, None, ref_windows)[0]
+        src = self.norm1(src + self.dropout1(attended))
+        ffn = self.linear2(self.dropout(self.activation(self.linear1(src))))
+        return self.norm2(src + self.dropout2(ffn))
+
+
+class TransformerEncoder(nn.Module):
+    def __init__(self, d_model, encoder_layer, num_layers):
+        super().__init__()
+        self.layers = get_clones(encoder_layer, num_layers)
+
+    def forward(self, src, pos, src_shape, src_start_idx, ref_windows):
+        for layer in self.layers:
+            src = layer(src, pos, src_shape, src_start_idx, ref_windows)
+        return src
+
+
+class TransformerDecoderLayer(nn.Module):
+    def __init__(self, d_model, nhead, nlevel, dim_feedforward, dropout, activation, backend=None):
+        super().__init__()
+        self.self_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout)
+        self.multihead_attn = Box3dAttention(d_model, nlevel, nhead, with_rotation=True, backend=backend)
+        self.pos_embed_layer = MLP(10, d_model, d_model, 3)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.norm3 = nn.LayerNorm(d_model)
+        self.dropout = nn.Dropout(dropout)
+        self.dropout1 = nn.Dropout(dropout)
+        self.dropout2 = nn.Dropout(dropout)
+        self.dropout3 = nn.Dropout(dropout)
+        self.activation = _act(activation)
+
+    def forward(self, idx, query, query_pos, memory, memory_shape, memory_start_idx, ref_windows, attn_mask=None):
+        if idx == 0:
+            # the first layer's content query IS the embedding of its reference window
+            query = self.pos_embed_layer(ref_windows)
+            q = k = query
+        elif query_pos is None:
+            query_pos = self.pos_embed_layer(ref_windows)
+            q = k = _add_pos(query, query_pos)
+        else:
+            q = k = _add_pos(query, query_pos)
+        sa = self.self_attn(q.transpose(0, 1), k.transpose(0, 1), query.transpose(0, 1), attn_mask=attn_mask)[0]
+        query = self.norm1(query + self.dropout1(sa.transpose(0, 1)))
+        ca = self.multihead_attn(_add_pos(query, query_pos), memory, memory_shape, None, memory_start_idx, None,
+                                 ref_windows[..., :7])[0]
+        query = self.norm2(query + self.dropout2(ca))
+        ffn = self.linear2(self.dropout(self.activation(self.linear1(query))))
+        return self.norm3(query + self.dropout3(ffn))
+
+
+class TransformerDecoder(nn.Module):
+    def __init__(self, d_model, decoder_layer, num_layers):
+        super().__init__()
+        self.layers = get_clones(decoder_layer, num_layers)
+        self.detection_head = None  # attached by the detector
+
+    def forward(self, query, query_pos, memory, memory_shape, memory_start_idx, ref_windows, attn_mask=None):
+        output = query
+        hidden, refs = [], []
+        for idx, layer in enumerate(self.layers):
+            output = layer(idx, output, query_pos, memory, memory_shape, memory_start_idx, ref_windows, attn_mask)
+            logits, new_windows = self.detection_head(output, ref_windows[..., :7], idx)
+            ref_windows = torch.cat((new_windows.detach(), logits.sigmoid().detach()), dim=-1)
+            hidden.append(output)
+            refs.append(new_windows)
+        return torch.stack(hidden), torch.stack(refs)
+
+
+class Transformer(nn.Module):
+    def __init__(self, d_model=256, nhead=8, nlevel=4, num_encoder_layers=6, num_decoder_layers=6,
+                 dim_feedforward=1024, dropout=0.1, activation="relu", num_queries=300, backend=None):
+        super().__init__()
+        self.num_queries = num_queries
+        enc = TransformerEncoderLayer(d_model, nhead, nlevel, dim_feedforward, dropout, activation, backend)
+        self.encoder = TransformerEncoder(d_model, enc, num_encoder_layers)
+        dec = TransformerDecoderLayer(d_model, nhead, nlevel, dim_feedforward, dropout, activation, backend)
+        self.decoder = TransformerDecoder(d_model, dec, num_decoder_layers)
+        self.proposal_head = None  # attached by the detector
+        self._ref_cache = {}
+
+    def _create_ref_windows(self, tensor_list):
+        """One (cx, cy, 0.5, 0.025, 0.025, 0.5, 0) window per BEV cell (VD/transformer.py:30-52)."""
+        out = []
+        for t in tensor_list:
+            B, _, H, W = t.shape
+            key = (H, W, t.device)
+            if key not in self._ref_cache:
+                ys = torch.linspace(0.5, H - 0.5, H, dtype=torch.float32, device=t.device)
+                xs = torch.linspace(0.5, W - 0.5, W, dtype=torch.float32, device=t.device)
+                ry, rx = torch.meshgrid(ys, xs, indexing="ij")
+                xy = torch.stack((rx.reshape(-1) / W, ry.reshape(-1) / H), -1)
+                z = torch.zeros_like(xy[:, :1])
+                self._ref_cache[key] = torch.cat((xy, z + 0.5, torch.ones_like(xy) * 0.025, z + 0.5, z), -1)
+            out.append(self._ref_cache[key][None].expand(B, -1, -1))
+        return torch.cat(out, dim=1)
+
+    def _get_enc_proposals(self, enc_embed, ref_windows):
+        logits, windows = self.proposal_head(enc_embed, ref_windows)
+        probs = logits[..., 0].sigmoid()
+        topk_probs, indexes = torch.topk(probs, self.num_queries, dim=1, sorted=False)
+        # the reference leaves the proposal order to topk(sorted=False); canonicalise it (ascending
+        # BEV index) so runs on different devices enumerate the same query set identically
+        indexes, order = indexes.sort(dim=1)
+        topk_probs = torch.gather(topk_probs, 1, order)
+        indexes = indexes.unsqueeze(-1)
+        windows = torch.gather(windows, 1, indexes.expand(-1, -1, windows.shape[-1]))
+        windows = torch.cat((windows.detach(), topk_probs.detach().unsqueeze(-1).expand(-1, -1, 3)), dim=-1)
+        return None, None, windows, indexes
+
+    def encode(self, src, pos):
+        assert pos is not None, "position encoding is required!"
+        anchors = self._create_ref_windows(src)
+        shapes = torch.tensor([[t.shape[2], t.shape[3]] for t in src], dtype=torch.int64, device=src[0].device)
+        flat = torch.cat([t.flatten(2).transpose(1, 2) for t in src], dim=1)
+        flat_pos = torch.cat([p.flatten(2).transpose(1, 2) for p in pos], dim=1)
+        start = torch.cat([shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]])
+        memory = self.encoder(flat, flat_pos, shapes, start, anchors)
+        return memory, anchors, shapes, start
+
+    def forward(self, src, pos):
+        memory, anchors, shapes, start = self.encode(src, pos)
+        query_embed, query_pos, proposals, topk_indexes = self._get_enc_proposals(memory, anchors)
+        hs, inter_refs = self.decoder(query_embed, query_pos, memory, shapes, start, proposals)
+        return hs, proposals[..., :7], inter_refs, memory, anchors, topk_indexes

@@ -35,6 +35,38 @@ def _check(t, name, dtype=None):
         raise RuntimeError("%s must have dtype %s, got %s" % (name, dtype, t.dtype))
 
 
+class KernelProfiler:
+    """Optional in-situ timing of the library's launches with CUDA events on the launching stream.
+    bench.py installs one for a few extra (untimed-for-throughput) steps to attribute time and
+    algorithmic bytes / flops per kernel family.  No effect when ``PROFILER`` is None."""
+
+    def __init__(self):
+        self.records = []  # (family, start_event, end_event, algorithmic_bytes, flops)
+
+    def begin(self):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
+
+    def end(self, family, start, nbytes, flops=0):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.records.append((family, start, ev, int(nbytes), int(flops)))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for fam, a, b, nbytes, flops in self.records:
+            d = out.setdefault(fam, {"launches": 0, "ms": 0.0, "bytes": 0, "flops": 0})
+            d["launches"] += 1
+            d["ms"] += a.elapsed_time(b)
+            d["bytes"] += nbytes
+            d["flops"] += flops
+        return out
+
+
+PROFILER = None
+
 _workspaces = {}
 
 
@@ -226,9 +258,14 @@ def spconv_forward(feats, w_kio, bias, nbr):
     m_out = nbr.shape[0]
     out = torch.empty((m_out, c_out), dtype=torch.float32, device=feats.device)
     L = _lib.lib()
+    t0 = PROFILER.begin() if PROFILER is not None else None
     rc = L.efgb_spconv_forward(_p(feats), feats.shape[0], c_in, _p(w_kio), _p(bias), _p(nbr), m_out, taps, c_out,
                                _p(out), _stream())
     _lib.check(rc, "spconv_forward")
+    if t0 is not None:
+        # algorithmic bytes: features in + out, weights, neighbour table
+        nbytes = 4 * (feats.shape[0] * c_in + m_out * c_out + taps * c_in * c_out + taps * m_out)
+        PROFILER.end("spconv_gemm_c%d" % max(c_in, c_out), t0, nbytes, 2 * m_out * taps * c_in * c_out)
     return out
 
 
@@ -238,9 +275,14 @@ def spconv_wgrad(feats, grad_out, nbr, taps, c_in, c_out):
     _check(nbr, "rulebook", torch.int32)
     dw = torch.empty((taps, c_in, c_out), dtype=torch.float32, device=feats.device)
     L = _lib.lib()
+    t0 = PROFILER.begin() if PROFILER is not None else None
     rc = L.efgb_spconv_wgrad(_p(feats), feats.shape[0], c_in, _p(grad_out), _p(nbr), nbr.shape[0], taps, c_out, _p(dw),
                              _stream())
     _lib.check(rc, "spconv_wgrad")
+    if t0 is not None:
+        m_out = nbr.shape[0]
+        nbytes = 4 * (feats.shape[0] * c_in + m_out * c_out + taps * c_in * c_out + taps * m_out)
+        PROFILER.end("spconv_wgrad_c%d" % max(c_in, c_out), t0, nbytes, 2 * m_out * taps * c_in * c_out)
     return dw
 
 
@@ -294,9 +336,13 @@ def box_attn_forward(value, shapes, level_start, loc, attn):
     b, lv, h, ch, nl, lq, npnt = _box_attn_shapes(value, shapes, level_start, loc, attn)
     out = torch.empty((b, lq, h * ch), dtype=torch.float32, device=value.device)
     L = _lib.lib()
+    t0 = PROFILER.begin() if PROFILER is not None else None
     rc = L.efgb_box_attn_forward(_p(value), _p(shapes), _p(level_start), _p(loc), _p(attn), b, lv, h, ch, nl, lq, npnt,
                                  _p(out), _stream())
     _lib.check(rc, "box_attn_forward")
+    if t0 is not None:
+        nbytes = 4 * (value.numel() + loc.numel() + attn.numel() + out.numel())
+        PROFILER.end("box_attn_fwd", t0, nbytes, 2 * b * lq * h * nl * npnt * 4 * ch)
     return out
 
 
@@ -307,7 +353,11 @@ def box_attn_backward(value, shapes, level_start, loc, attn, grad_out):
     grad_loc = torch.empty_like(loc)
     grad_attn = torch.empty_like(attn)
     L = _lib.lib()
+    t0 = PROFILER.begin() if PROFILER is not None else None
     rc = L.efgb_box_attn_backward(_p(value), _p(shapes), _p(level_start), _p(loc), _p(attn), _p(grad_out), b, lv, h, ch,
                                   nl, lq, npnt, _p(grad_value), _p(grad_loc), _p(grad_attn), _stream())
     _lib.check(rc, "box_attn_backward")
+    if t0 is not None:
+        nbytes = 4 * (2 * value.numel() + 2 * loc.numel() + 2 * attn.numel() + grad_out.numel())
+        PROFILER.end("box_attn_bwd", t0, nbytes, 6 * b * lq * h * nl * npnt * 4 * ch)
     return grad_value, grad_loc, grad_attn

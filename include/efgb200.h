@@ -39,6 +39,8 @@ typedef void* efgb_stream_t; /* cudaStream_t */
 
 const char* efgb_last_error(void);
 int efgb_version(void);
+/* number of CUDA kernels this library has launched in this process (monotonic; for bench accounting) */
+uint64_t efgb_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Voxelizer — first-come "hard" voxelization, bit-exact with the reference's CPU twins

@@ -120,7 +120,7 @@ def canonical_pairs(nbr, in_coords, out_coords):
 def conv(feats, weight, bias, nbr):
     """feats [Mi,Cin] torch f32, weight [Cout,kd,kh,kw,Cin] (spconv 2.x layout), nbr [Mo,K] -> [Mo,Cout].
     Per-tap gather - mm - index_add (spconv's 'native' algorithm); differentiable through torch."""
-    nbr_t = torch.as_tensor(np.asarray(nbr), dtype=torch.long)
+    nbr_t = torch.as_tensor(np.asarray(nbr), dtype=torch.long).to(feats.device)
     c_out = weight.shape[0]
     taps = nbr_t.shape[1]
     w = weight.reshape(c_out, taps, -1)
@@ -153,6 +153,6 @@ def dense_conv_at_sites(feats, in_coords, batch, in_dhw, weight, bias, stride, p
 def to_dense(feats, coords, batch, dhw):
     d, h, w = [int(x) for x in dhw]
     dense = feats.new_zeros((batch, feats.shape[1], d, h, w))
-    c = torch.as_tensor(np.asarray(coords), dtype=torch.long)
+    c = torch.as_tensor(np.asarray(coords), dtype=torch.long).to(feats.device)
     dense[c[:, 0], :, c[:, 1], c[:, 2], c[:, 3]] = feats
     return dense

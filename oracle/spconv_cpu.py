@@ -85,7 +85,7 @@ class _Conv(SparseModule):
         else:
             oc, out_shape, nbr, _ = sc.sparse_rulebook(coords, x.batch_size, x.spatial_shape, self.kernel_size,
                                                        self.stride, self.padding)
-            out_idx = torch.from_numpy(oc)
+            out_idx = torch.from_numpy(oc).to(x.indices.device)
         feats = sc.conv(x.features, self.weight, self.bias, nbr)
         return SparseConvTensor(feats, out_idx, out_shape, x.batch_size, x.indice_dict)
 

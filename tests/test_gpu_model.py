@@ -1,0 +1,133 @@
+"""GPU parity, whole model: Voxel-DETR on the CUDA backend vs the SAME module graph on the CPU
+oracle backend, identical weights and synthetic scene.  north_star tolerance: logits / boxes within
+1e-3 (fp32)."""
+import numpy as np
+import pytest
+import torch
+
+from efg_b200.detectors.voxel_detr import VoxelDETR
+from oracle.backend_cpu import cpu_backend, voxelized_sample
+from test_model_cpu import small_batch, small_config
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+@pytest.fixture(autouse=True)
+def _fp32_library_math():
+    """The oracle is plain fp32; torch's cuDNN convolutions default to TF32 on the GPU (as they would
+    for the reference too).  Parity is checked with the library layers in fp32."""
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+class _ReplayMatcher:
+    """At random initialisation all queries are nearly identical, so the Hungarian cost matrix is
+    nearly degenerate and 1e-6 differences flip assignments.  To compare kernels rather than
+    tie-breaking, the GPU run replays the assignments of the CPU run."""
+
+    def __init__(self):
+        self.log = []
+        self.replay = None
+
+    def install(self, model, record):
+        from efg_b200.detectors.voxel_detr.matcher import HungarianMatcher3d
+
+        orig = HungarianMatcher3d.solve
+        me = self
+
+        def solve(mats):
+            if record:
+                out = orig(mats)
+                me.log.append(out)
+                return out
+            return me.replay.pop(0)
+
+        for head in (model.transformer.proposal_head, model.transformer.decoder.detection_head):
+            head.losses.matcher.solve = solve
+
+
+def _models(num_queries=40):
+    torch.manual_seed(0)
+    cpu = VoxelDETR(small_config("cpu", num_queries), backend=cpu_backend())
+    gpu = VoxelDETR(small_config("cuda", num_queries))
+    gpu.load_state_dict(cpu.state_dict())
+    return cpu, gpu
+
+
+def test_voxel_detr_eval_parity_points_in_voxels_out():
+    cpu, gpu = _models()
+    cpu.eval()
+    gpu.eval()
+    scenes = small_batch(2, 6000, seed=3)
+    cfg = cpu.config
+    batch_cpu = [(voxelized_sample(p, cfg.dataset), {"annotations": a}) for p, a in scenes]
+    batch_gpu = [({"points": p}, {"annotations": a}) for p, a in scenes]  # voxelized on the GPU
+    with torch.no_grad():
+        fc, _ = cpu.extract(batch_cpu)
+        fg, _ = gpu.extract(batch_gpu)
+        assert (fg[0].cpu() - fc[0]).abs().max().item() < TOL
+        hc = cpu.transformer(fc, [cpu.backbone.position_encoding(fc[0])])
+        hg = gpu.transformer(fg, [gpu.backbone.position_encoding(fg[0])])
+    # encoder memory
+    assert (hg[3].cpu() - hc[3]).abs().max().item() < TOL
+    # proposals are a top-k with sorted=False: compare as sets, then align the decoder outputs by index
+    ic, ig = hc[5].squeeze(-1), hg[5].squeeze(-1).cpu()
+    for b in range(ic.shape[0]):
+        oc, og = torch.argsort(ic[b]), torch.argsort(ig[b])
+        assert torch.equal(ic[b][oc], ig[b][og])
+        assert (hg[0][:, b].cpu()[:, og] - hc[0][:, b][:, oc]).abs().max().item() < TOL      # hidden states
+        assert (hg[2][:, b].cpu()[:, og] - hc[2][:, b][:, oc]).abs().max().item() < TOL      # refined boxes
+        head_c, head_g = cpu.transformer.decoder.detection_head, gpu.transformer.decoder.detection_head
+        lc, bc = head_c(hc[0][-1, b][oc], hc[2][-2, b][oc], 1)
+        lg, bg = head_g(hg[0][-1, b][og.cuda()], hg[2][-2, b][og.cuda()], 1)
+        assert (lg.cpu() - lc).abs().max().item() < TOL and (bg.cpu() - bc).abs().max().item() < TOL
+
+
+def test_voxel_detr_train_step_parity():
+    """Losses must agree to 1e-4.  Gradients of this graph at random initialisation are
+    ill-conditioned: the SAME CPU oracle model evaluated in fp32 and in fp64 differs by ~7 % (median)
+    in its gradients while its loss agrees to 7 digits (measured, DESIGN.md "parity notes").  Gradient
+    parity of the kernels themselves is asserted where conditioning is benign (test_gpu_spconv.py,
+    test_gpu_box_attn.py); here the CUDA path has to be as close to the CPU oracle as the oracle's own
+    torch graph is when it merely runs on another device (the noise floor)."""
+    cpu, gpu = _models()
+    torch.manual_seed(0)
+    gpo = VoxelDETR(small_config("cuda", 40), backend=cpu_backend())  # oracle ops (plain torch) on the GPU
+    gpo.load_state_dict(cpu.state_dict())
+    for m in (cpu, gpu, gpo):
+        m.train()
+    scenes = small_batch(2, 6000, seed=11)
+    cfg = cpu.config
+    rm = _ReplayMatcher()
+    rm.install(cpu, record=True)
+    lc = cpu([(voxelized_sample(p, cfg.dataset), {"annotations": a}) for p, a in scenes])
+    rm.replay = list(rm.log)
+    rm.install(gpu, record=False)
+    lg = gpu([({"points": p}, {"annotations": a}) for p, a in scenes])
+    rm.replay = list(rm.log)
+    rm.install(gpo, record=False)
+    lo = gpo([({"points": p}, {"annotations": a}) for p, a in scenes])
+    assert set(lc) == set(lg)
+    for k in lc:
+        if k.startswith("loss"):
+            assert abs(float(lg[k]) - float(lc[k])) < 1e-4 * max(1.0, abs(float(lc[k]))), (k, float(lg[k]), float(lc[k]))
+    for losses in (lc, lg, lo):
+        sum(v for k, v in losses.items() if k.startswith("loss")).backward()
+    pc, pg, po = dict(cpu.named_parameters()), dict(gpu.named_parameters()), dict(gpo.named_parameters())
+    checked = 0
+    for name, ref in pc.items():
+        gc, gg, go = ref.grad, pg[name].grad, po[name].grad
+        assert (gc is None) == (gg is None), name
+        if gc is None:
+            continue
+        scale = max(float(gc.abs().max()), 1e-12)
+        err = float((gg.cpu() - gc).abs().max()) / scale
+        floor = float((go.cpu() - gc).abs().max()) / scale
+        assert err < max(3.0 * floor, 2e-3), (name, err, floor)
+        checked += 1
+    assert checked > 150
