@@ -1,0 +1,481 @@
+// Sparse convolution forward / dgrad on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Output-stationary implicit GEMM over the device rulebook:
+//     D[128 output rows x N] = sum over K = (tap, channel)  A[row, K] * B[n, K]
+//   A[row, (tap, c)] = in[nbr[row, tap], c]     gathered on the fly (zeros where nbr = -1)
+//   B[n,   (tap, c)] = weight element           pre-packed once per call into the exact shared-memory
+//                                               image (K-major, 128-byte swizzle) the tensor core reads
+// K is consumed in chunks of 32 floats = one 128-byte swizzled row per operand row.
+//
+// Roles inside one persistent CTA (one CTA per SM, tiles strided over the grid):
+//   warps 0-7   A producers: 8 lanes gather one 128-byte row piece with coalesced LDG.128, split it
+//               into tf32 hi/lo parts, and store it swizzled into the stage's A tiles
+//   warp  8     MMA issuer: one elected lane issues tcgen05.mma.kind::tf32 (M=128, N, K=8) into TMEM;
+//               tcgen05.commit releases the stage / publishes the accumulator
+//   warp  9     B loader: one lane streams the packed weight chunk with cp.async.bulk (TMA engine,
+//               mbarrier complete_tx) — weights stay L2-resident
+//   warps 10-13 epilogue: tcgen05.ld the fp32 accumulator (double-buffered in TMEM), add bias, store rows
+//
+// Precision: kSplit = true runs the 3xTF32 scheme (a = a_hi + a_lo, b = b_hi + b_lo;
+// a_hi*b_hi + a_lo*b_hi + a_hi*b_lo with fp32 accumulation), error ~2^-21 relative, i.e. fp32-faithful
+// (the reference runs this path in fp32).  kSplit = false is single-pass TF32.
+#include "common.cuh"
+
+namespace efgb {
+namespace tc {
+
+constexpr int kTileM = 128;
+constexpr int kChunkK = 32;             // floats per K chunk (128 bytes)
+constexpr int kProducerWarps = 8;
+constexpr int kMmaWarp = 8;
+constexpr int kLoaderWarp = 9;
+constexpr int kThreads = 14 * 32;
+constexpr int kMaxTaps = 32;
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzle shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp:SmemDescriptor):
+// start>>4 [0,14), LBO>>4 [16,30) (unused for swizzled K-major), SBO>>4 [32,46) = 1024 B between 8-row
+// groups, version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// kind::tf32 instruction descriptor (mma_sm100_desc.hpp:InstrDescriptor): D=f32 [4,6)=1, A=tf32 [7,10)=2,
+// B=tf32 [10,13)=2, both K-major, N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+struct Params {
+  const float* in;       // [num_in, c_red]
+  const float* packed;   // [chunks][parts][n_out][32] swizzled image
+  const float* bias;     // [n_out] or null
+  const int32_t* nbr;    // [num_out, taps]
+  float* out;            // [num_out, n_out]
+  int64_t num_out;
+  int c_red, taps, n_out, chunks;
+  int num_tiles;
+};
+
+template <bool kSplit>
+struct Smem {
+  static constexpr int kParts = kSplit ? 2 : 1;
+  static __host__ __device__ int a_bytes() { return kParts * kTileM * 128; }
+  static __host__ __device__ int b_bytes(int n) { return kParts * n * 128; }
+  static __host__ __device__ int stage_bytes(int n) { return a_bytes() + b_bytes(n); }
+};
+
+__host__ inline int pick_stages(int stage_bytes, int nbr_bytes) {
+  const int budget = 227 * 1024 - 2048 - nbr_bytes;
+  int s = budget / stage_bytes;
+  if (s > 6) s = 6;
+  return s;
+}
+
+template <bool kSplit>
+__global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p, const int stages) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the swizzle atoms
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int stage_bytes = Smem<kSplit>::stage_bytes(p.n_out);
+  const int a_part = kTileM * 128;
+  const int b_part = p.n_out * 128;
+  uint8_t* stage_base = smem;
+  int32_t* s_nbr = reinterpret_cast<int32_t*>(smem + static_cast<size_t>(stages) * stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_nbr) + ((kTileM * p.taps * 4 + 15) & ~15));
+  // bars: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then the TMEM base word
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + stages;
+  uint64_t* tmem_full = bars + 2 * stages;
+  uint64_t* tmem_empty = bars + 2 * stages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // TMEM columns: two accumulators of n_out fp32 columns, power of two >= 32
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(2 * p.n_out)) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), kProducerWarps + 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tmem_full[a]), 1);
+      mbar_init(smem_u32(&tmem_empty[a]), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kProducerWarps) {
+    // ================= A producers =================
+    int stage = 0;
+    uint32_t phase = 0;
+    const int row_in_group = lane >> 3;  // 0..3
+    const int q = lane & 7;              // 16-byte piece of the 128-byte row
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int64_t r0 = static_cast<int64_t>(tile) * kTileM;
+      // stage the tile's slice of the rulebook (producer warps only: named barrier 1)
+      asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory");
+      {
+        const int total = kTileM * p.taps;
+        const int64_t limit = (p.num_out - r0) * p.taps;
+        const int32_t* src = p.nbr + r0 * p.taps;
+        for (int e = threadIdx.x; e < total; e += kProducerWarps * 32) s_nbr[e] = e < limit ? src[e] : -1;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory");
+
+      for (int c = 0; c < p.chunks; ++c) {
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        uint8_t* a_hi = stage_base + static_cast<size_t>(stage) * stage_bytes;
+        uint8_t* a_lo = a_hi + a_part;
+        const int kk = c * kChunkK + q * 4;  // first K index of this lane's 16-byte piece
+        const int tap = kk / p.c_red;
+        const int ci = kk - tap * p.c_red;
+        const bool tap_ok = tap < p.taps;
+        float4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = (i * kProducerWarps + warp) * 4 + row_in_group;
+          const int32_t src = tap_ok ? s_nbr[r * p.taps + tap] : -1;
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (src >= 0) v[i] = __ldg(reinterpret_cast<const float4*>(p.in + static_cast<int64_t>(src) * p.c_red + ci));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = (i * kProducerWarps + warp) * 4 + row_in_group;
+          const uint32_t off = static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(q ^ (r & 7)) << 4);
+          if (kSplit) {
+            float4 hi, lo;
+            hi.x = __uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u);
+            hi.y = __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u);
+            hi.z = __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u);
+            hi.w = __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u);
+            lo.x = v[i].x - hi.x;
+            lo.y = v[i].y - hi.y;
+            lo.z = v[i].z - hi.z;
+            lo.w = v[i].w - hi.w;
+            *reinterpret_cast<float4*>(a_hi + off) = hi;
+            *reinterpret_cast<float4*>(a_lo + off) = lo;
+          } else {
+            *reinterpret_cast<float4*>(a_hi + off) = v[i];
+          }
+        }
+        fence_proxy_async();  // make the generic-proxy stores visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == kLoaderWarp) {
+    // ================= B loader (TMA bulk copies of the packed weight chunks) =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t b_bytes = static_cast<uint32_t>(Smem<kSplit>::b_bytes(p.n_out));
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int c = 0; c < p.chunks; ++c) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t bar = smem_u32(&full_bar[stage]);
+          mbar_arrive_expect_tx(bar, b_bytes);
+          const uint32_t dst = smem_u32(stage_base + static_cast<size_t>(stage) * stage_bytes + Smem<kSplit>::a_bytes());
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.packed) + static_cast<size_t>(c) * b_bytes;
+          for (uint32_t o = 0; o < b_bytes; o += 16384u) {
+            const uint32_t n = b_bytes - o < 16384u ? b_bytes - o : 16384u;
+            bulk_g2s(dst + o, src + o, n, bar);
+          }
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kMmaWarp) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase[2] = {0, 0};
+      const uint32_t idesc = make_idesc_tf32(kTileM, p.n_out);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase[acc] ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * p.n_out);
+        for (int c = 0; c < p.chunks; ++c) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(stage_base + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t b_hi = a_hi + Smem<kSplit>::a_bytes();
+          const uint64_t da_hi = make_desc_sw128(a_hi);
+          const uint64_t db_hi = make_desc_sw128(b_hi);
+          const uint64_t da_lo = make_desc_sw128(a_hi + a_part);
+          const uint64_t db_lo = make_desc_sw128(b_hi + b_part);
+#pragma unroll
+          for (int j = 0; j < kChunkK / 8; ++j) {
+            const uint64_t adv = static_cast<uint64_t>(j * 2);  // 8 tf32 = 32 bytes = 2 x 16 B
+            if (kSplit) {
+              tc_mma_tf32(tmem_d, da_lo + adv, db_hi + adv, idesc, (c | j) ? 1u : 0u);
+              tc_mma_tf32(tmem_d, da_hi + adv, db_lo + adv, idesc, 1u);
+              tc_mma_tf32(tmem_d, da_hi + adv, db_hi + adv, idesc, 1u);
+            } else {
+              tc_mma_tf32(tmem_d, da_hi + adv, db_hi + adv, idesc, (c | j) ? 1u : 0u);
+            }
+          }
+          tc_commit(smem_u32(&empty_bar[stage]));  // stage reusable once these MMAs have read it
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(smem_u32(&tmem_full[acc]));  // accumulator complete
+        acc_phase[acc] ^= 1;
+        acc ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue (4 warps; warp w may only touch TMEM lanes 32*(w%4)..+31) =================
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase[2] = {0, 0};
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(smem_u32(&tmem_full[acc]), acc_phase[acc]);
+      tc_fence_after();
+      const int64_t row = static_cast<int64_t>(tile) * kTileM + quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * p.n_out);
+      for (int c0 = 0; c0 < p.n_out; c0 += 16) {
+        uint32_t r[16];
+        tc_ld16(taddr + c0, r);
+        tc_wait_ld();
+        if (row < p.num_out) {
+          float* dst = p.out + row * p.n_out + c0;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 o;
+            o.x = __uint_as_float(r[j + 0]) + (p.bias ? p.bias[c0 + j + 0] : 0.f);
+            o.y = __uint_as_float(r[j + 1]) + (p.bias ? p.bias[c0 + j + 1] : 0.f);
+            o.z = __uint_as_float(r[j + 2]) + (p.bias ? p.bias[c0 + j + 2] : 0.f);
+            o.w = __uint_as_float(r[j + 3]) + (p.bias ? p.bias[c0 + j + 3] : 0.f);
+            *reinterpret_cast<float4*>(dst + j) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
+      acc_phase[acc] ^= 1;
+      acc ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// Pack weights (reference parameter layout [c_out, taps, c_in]) into the swizzled K-major chunk image.
+//   mode 0: forward        B[n = co][(tap, c = ci)] = w[co][tap][ci]            (N = c_out, c_red = c_in)
+//   mode 1: dgrad          B[n = ci][(tap, c = co)] = w[co][tap][ci]            (N = c_in,  c_red = c_out)
+//   mode 2: dgrad, subm    B[n = ci][(tap, c = co)] = w[co][taps-1-tap][ci]     (tap mirrored, see spconv/pytorch.py)
+template <bool kSplit>
+__global__ void __launch_bounds__(256)
+pack_weights_kernel(const float* __restrict__ w, int c_out, int taps, int c_in, int mode, int n_out, int c_red, int chunks,
+                    float* __restrict__ packed) {
+  constexpr int kParts = kSplit ? 2 : 1;
+  const int64_t total = static_cast<int64_t>(chunks) * n_out * kChunkK;
+  int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int kk = static_cast<int>(t % kChunkK);
+  const int n = static_cast<int>((t / kChunkK) % n_out);
+  const int chunk = static_cast<int>(t / (static_cast<int64_t>(kChunkK) * n_out));
+  const int kidx = chunk * kChunkK + kk;
+  const int tap = kidx / c_red;
+  const int c = kidx - tap * c_red;
+  float v = 0.f;
+  if (tap < taps) {
+    if (mode == 0) {
+      if (n < c_out) v = w[(static_cast<int64_t>(n) * taps + tap) * c_in + c];
+    } else {
+      const int st = mode == 2 ? taps - 1 - tap : tap;
+      if (n < c_in) v = w[(static_cast<int64_t>(c) * taps + st) * c_in + n];
+    }
+  }
+  const int qphys = (kk >> 2) ^ (n & 7);
+  const int64_t off = static_cast<int64_t>(n) * kChunkK + qphys * 4 + (kk & 3);
+  float* base = packed + static_cast<int64_t>(chunk) * kParts * n_out * kChunkK;
+  if (kSplit) {
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    base[off] = hi;
+    base[static_cast<int64_t>(n_out) * kChunkK + off] = v - hi;
+  } else {
+    base[off] = v;
+  }
+}
+
+static bool supported(int c_red, int n_out, int taps) {
+  return c_red >= 4 && c_red % 4 == 0 && n_out >= 16 && n_out <= 256 && n_out % 16 == 0 && taps >= 1 && taps <= kMaxTaps;
+}
+
+static int chunks_for(int taps, int c_red) { return (taps * c_red + kChunkK - 1) / kChunkK; }
+
+}  // namespace tc
+}  // namespace efgb
+
+using namespace efgb;
+
+extern "C" int efgb_spconv_tc_supported(int c_red, int n_out, int taps) { return tc::supported(c_red, n_out, taps) ? 1 : 0; }
+
+extern "C" size_t efgb_spconv_tc_packed_bytes(int taps, int c_red, int n_out, int split) {
+  if (!tc::supported(c_red, n_out, taps)) return 0;
+  return static_cast<size_t>(tc::chunks_for(taps, c_red)) * (split ? 2 : 1) * n_out * tc::kChunkK * sizeof(float);
+}
+
+extern "C" int efgb_spconv_tc_pack(const float* w_param, int c_out, int taps, int c_in, int mode, int split, float* packed,
+                                   efgb_stream_t stream_) {
+  cudaStream_t stream = as_stream(stream_);
+  EFGB_REQUIRE(w_param && packed && mode >= 0 && mode <= 2, EFGB_EINVAL, "spconv_tc_pack: bad argument");
+  const int n_out = mode == 0 ? c_out : c_in;
+  const int c_red = mode == 0 ? c_in : c_out;
+  EFGB_REQUIRE(tc::supported(c_red, n_out, taps), EFGB_EINVAL, "spconv_tc_pack: unsupported shape (c_red=%d n_out=%d taps=%d)",
+               c_red, n_out, taps);
+  const int chunks = tc::chunks_for(taps, c_red);
+  const int64_t total = static_cast<int64_t>(chunks) * n_out * tc::kChunkK;
+  const unsigned nb = static_cast<unsigned>((total + 255) / 256);
+  if (split)
+    tc::pack_weights_kernel<true><<<nb, 256, 0, stream>>>(w_param, c_out, taps, c_in, mode, n_out, c_red, chunks, packed);
+  else
+    tc::pack_weights_kernel<false><<<nb, 256, 0, stream>>>(w_param, c_out, taps, c_in, mode, n_out, c_red, chunks, packed);
+  EFGB_LAUNCH_OK("pack_weights_kernel");
+  return EFGB_OK;
+}
+
+extern "C" int efgb_spconv_tc_forward(const float* in_feats, int64_t num_in, int c_red, const float* packed,
+                                      const float* bias, const int32_t* nbr, int64_t num_out, int taps, int n_out,
+                                      int split, float* out_feats, efgb_stream_t stream_) {
+  cudaStream_t stream = as_stream(stream_);
+  EFGB_REQUIRE(tc::supported(c_red, n_out, taps), EFGB_EINVAL, "spconv_tc_forward: unsupported shape (c_red=%d n_out=%d taps=%d)",
+               c_red, n_out, taps);
+  EFGB_REQUIRE(num_in >= 0 && num_out >= 0, EFGB_EINVAL, "spconv_tc_forward: bad sizes");
+  if (num_out == 0) return EFGB_OK;
+  EFGB_REQUIRE(packed && nbr && out_feats && (in_feats || num_in == 0), EFGB_EINVAL, "spconv_tc_forward: null pointer");
+  EFGB_REQUIRE((reinterpret_cast<uintptr_t>(in_feats) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_feats) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(packed) & 15) == 0,
+               EFGB_EINVAL, "spconv_tc_forward: feature / weight pointers must be 16-byte aligned");
+  tc::Params p;
+  p.in = in_feats;
+  p.packed = packed;
+  p.bias = bias;
+  p.nbr = nbr;
+  p.out = out_feats;
+  p.num_out = num_out;
+  p.c_red = c_red;
+  p.taps = taps;
+  p.n_out = n_out;
+  p.chunks = tc::chunks_for(taps, c_red);
+  p.num_tiles = static_cast<int>((num_out + tc::kTileM - 1) / tc::kTileM);
+  const int nbr_bytes = (tc::kTileM * taps * 4 + 15) & ~15;
+  const int stage_bytes = split ? tc::Smem<true>::stage_bytes(n_out) : tc::Smem<false>::stage_bytes(n_out);
+  const int stages = tc::pick_stages(stage_bytes, nbr_bytes);
+  EFGB_REQUIRE(stages >= 2, EFGB_EINVAL, "spconv_tc_forward: tile does not fit shared memory");
+  const size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + nbr_bytes + (2 * stages + 4) * 8 + 16;
+  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  if (split) {
+    static bool configured = false;
+    if (!configured) {
+      EFGB_CUDA_OK(cudaFuncSetAttribute(tc::spconv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      configured = true;
+    }
+    tc::spconv_tc_kernel<true><<<grid, tc::kThreads, smem, stream>>>(p, stages);
+  } else {
+    static bool configured = false;
+    if (!configured) {
+      EFGB_CUDA_OK(cudaFuncSetAttribute(tc::spconv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      configured = true;
+    }
+    tc::spconv_tc_kernel<false><<<grid, tc::kThreads, smem, stream>>>(p, stages);
+  }
+  EFGB_LAUNCH_OK("spconv_tc_kernel");
+  return EFGB_OK;
+}

@@ -269,6 +269,48 @@ def spconv_forward(feats, w_kio, bias, nbr):
     return out
 
 
+# "fp32x3": tensor cores with the 3xTF32 split (fp32-faithful, default); "tf32": single-pass TF32;
+# "simt": exact fp32 FFMA kernel everywhere.
+CONV_PRECISION = "fp32x3"
+
+
+def spconv_tc_supported(c_red, n_out, taps):
+    return CONV_PRECISION != "simt" and c_red >= 16 and bool(_lib.lib().efgb_spconv_tc_supported(c_red, n_out, taps))
+
+
+def spconv_tc(feats, w_param, bias, nbr, mode):
+    """Tensor-core gather-GEMM.  w_param [c_out, taps, c_in] (reference layout), mode 0 fwd / 1 dgrad /
+    2 dgrad-submanifold; feats [Mi, c_red]; returns [nbr.shape[0], N]."""
+    _check(feats, "features", torch.float32)
+    _check(w_param, "weight", torch.float32)
+    _check(nbr, "rulebook", torch.int32)
+    c_out, taps, c_in = w_param.shape
+    n_out, c_red = (c_out, c_in) if mode == 0 else (c_in, c_out)
+    if feats.shape[1] != c_red or nbr.shape[1] != taps:
+        raise RuntimeError("spconv_tc: shape mismatch feats %r weight %r rulebook %r mode %d" %
+                           (tuple(feats.shape), tuple(w_param.shape), tuple(nbr.shape), mode))
+    split = 1 if CONV_PRECISION == "fp32x3" else 0
+    L = _lib.lib()
+    dev = feats.device
+    packed = torch.empty(L.efgb_spconv_tc_packed_bytes(taps, c_red, n_out, split) // 4, dtype=torch.float32, device=dev)
+    m_out = nbr.shape[0]
+    out = torch.empty((m_out, n_out), dtype=torch.float32, device=dev)
+    t0 = PROFILER.begin() if PROFILER is not None else None
+    _lib.check(L.efgb_spconv_tc_pack(_p(w_param), c_out, taps, c_in, mode, split, _p(packed), _stream()), "spconv_tc_pack")
+    if t0 is not None:
+        PROFILER.end("spconv_pack_weights", t0, 4 * (w_param.numel() + packed.numel()))
+        t0 = PROFILER.begin()
+    if bias is not None:
+        _check(bias, "bias", torch.float32)
+    rc = L.efgb_spconv_tc_forward(_p(feats), feats.shape[0], c_red, _p(packed), _p(bias), _p(nbr), m_out, taps, n_out,
+                                  split, _p(out), _stream())
+    _lib.check(rc, "spconv_tc_forward")
+    if t0 is not None:
+        nbytes = 4 * (feats.shape[0] * c_red + m_out * n_out + taps * c_red * n_out + taps * m_out)
+        PROFILER.end("spconv_tc_c%d" % max(c_red, n_out), t0, nbytes, 2 * m_out * taps * c_red * n_out)
+    return out
+
+
 def spconv_wgrad(feats, grad_out, nbr, taps, c_in, c_out):
     _check(feats, "features", torch.float32)
     _check(grad_out, "grad_out", torch.float32)

@@ -97,34 +97,42 @@ class _ToDenseFn(Function):
 
 class _SparseConvFn(Function):
     """out = conv(features) over a rulebook; backward = dgrad (same kernel on the transposed
-    rulebook) + wgrad.  Weight is tap-major [K, Cin, Cout] here; the module permutes."""
+    rulebook) + wgrad.  ``weight`` is the parameter viewed as [Cout, taps, Cin]."""
 
     @staticmethod
-    def forward(ctx, features, w_kio, bias, rulebook):
+    def forward(ctx, features, weight, bias, rulebook):
         features = features.contiguous()
-        out = ops.spconv_forward(features, w_kio, bias, rulebook.nbr)
+        weight = weight.contiguous()
+        c_out, taps, c_in = weight.shape
+        if ops.spconv_tc_supported(c_in, c_out, taps):
+            out = ops.spconv_tc(features, weight, bias, rulebook.nbr, 0)
+        else:
+            out = ops.spconv_forward(features, weight.permute(1, 2, 0).contiguous(), bias, rulebook.nbr)
         ctx.rulebook = rulebook
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(features, w_kio)
+        ctx.save_for_backward(features, weight)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        features, w_kio = ctx.saved_tensors
+        features, weight = ctx.saved_tensors
         rb = ctx.rulebook
         grad_out = grad_out.contiguous()
-        taps, c_in, c_out = w_kio.shape
+        c_out, taps, c_in = weight.shape
         d_feat = d_w = d_b = None
         if ctx.needs_input_grad[0]:
-            if rb.subm:
-                # nbr[j, K-1-k] is the output that input j feeds through tap k (odd kernels are symmetric)
-                w_t = w_kio.flip(0).transpose(1, 2).contiguous()
-                d_feat = ops.spconv_forward(grad_out, w_t, None, rb.nbr)
+            # submanifold: nbr[j, K-1-k] is the output that input j feeds through tap k (odd kernels are
+            # symmetric), so dgrad reuses the forward table with mirrored taps; regular: transposed table
+            table = rb.nbr if rb.subm else rb.nbr_t
+            if ops.spconv_tc_supported(c_out, c_in, taps):
+                d_feat = ops.spconv_tc(grad_out, weight, None, table, 2 if rb.subm else 1)
             else:
-                w_t = w_kio.transpose(1, 2).contiguous()
-                d_feat = ops.spconv_forward(grad_out, w_t, None, rb.nbr_t)
+                w_t = weight.permute(1, 0, 2)  # [taps, Cout, Cin]
+                if rb.subm:
+                    w_t = w_t.flip(0)
+                d_feat = ops.spconv_forward(grad_out, w_t.contiguous(), None, table)
         if ctx.needs_input_grad[1]:
-            d_w = ops.spconv_wgrad(features, grad_out, rb.nbr, taps, c_in, c_out)
+            d_w = ops.spconv_wgrad(features, grad_out, rb.nbr, taps, c_in, c_out).permute(2, 0, 1).contiguous()
         if ctx.has_bias and ctx.needs_input_grad[2]:
             d_b = grad_out.sum(0)
         return d_feat, d_w, d_b, None
@@ -249,8 +257,7 @@ class SparseConvolution(SparseModule):
         assert isinstance(x, SparseConvTensor), "sparse convolution expects a SparseConvTensor"
         rb = self._rulebook(x)
         taps = self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2]
-        w_kio = self.weight.reshape(self.out_channels, taps, self.in_channels).permute(1, 2, 0).contiguous()
-        feats = _SparseConvFn.apply(x.features, w_kio, self.bias, rb)
+        feats = _SparseConvFn.apply(x.features, self.weight.view(self.out_channels, taps, self.in_channels), self.bias, rb)
         out = SparseConvTensor(feats, rb.out_indices, rb.out_shape, x.batch_size, x.grid, x.voxel_num, x.indice_dict,
                                x.benchmark)
         out._rows_sorted = x._rows_sorted if self.subm else True

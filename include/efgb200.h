@@ -149,6 +149,26 @@ int efgb_spconv_forward(const float* in_feats, int64_t num_in, int c_in,
                         const int32_t* nbr, int64_t num_out, int num_taps, int c_out,
                         float* out_feats, efgb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Tensor-core path of the same gather-GEMM (tcgen05.mma kind::tf32, accumulators in TMEM, weights
+ * streamed by the TMA engine).  Weights are given in the reference parameter layout
+ * [c_out, taps, c_in] (spconv 2.x, taps = kd*kh*kw flattened) and packed once per call into the
+ * shared-memory image the tensor core reads:
+ *   mode 0 forward            N = c_out, reduction channels c_red = c_in
+ *   mode 1 dgrad (regular)    N = c_in,  c_red = c_out   (use with nbr_t)
+ *   mode 2 dgrad (submanifold, tap order mirrored; use with the forward nbr)
+ * split != 0 selects 3xTF32 (fp32-faithful, error ~2^-21); split == 0 single-pass TF32.
+ * Supported when c_red % 4 == 0, 16 <= N <= 256, N % 16 == 0, taps <= 32.
+ * ------------------------------------------------------------------------------------------ */
+int efgb_spconv_tc_supported(int c_red, int n_out, int taps);
+size_t efgb_spconv_tc_packed_bytes(int taps, int c_red, int n_out, int split);
+int efgb_spconv_tc_pack(const float* w_param, int c_out, int taps, int c_in, int mode, int split,
+                        float* packed, efgb_stream_t stream);
+int efgb_spconv_tc_forward(const float* in_feats, int64_t num_in, int c_red, const float* packed,
+                           const float* bias /* nullable [n_out] */, const int32_t* nbr,
+                           int64_t num_out, int taps, int n_out, int split, float* out_feats,
+                           efgb_stream_t stream);
+
 /* dw[k, ci, co] = sum_o in[nbr[o,k], ci] * grad_out[o, co]; dw is zero-filled by the callee. */
 int efgb_spconv_wgrad(const float* in_feats, int64_t num_in, int c_in,
                       const float* grad_out, const int32_t* nbr, int64_t num_out, int num_taps,

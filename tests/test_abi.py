@@ -69,3 +69,24 @@ def test_product_never_imports_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M) or "oracle/" in src:
                     bad.append(os.path.join(dirpath, f))
     assert not bad, "product files reference the oracle: %s" % bad
+
+
+def test_compat_aliases():
+    import sys
+
+    from efg_b200 import compat
+
+    names = compat.install()
+    assert "spconv.pytorch" in names
+    import spconv.pytorch as sp
+    from spconv.pytorch import SparseConv3d, SubMConv3d  # noqa: F401  (the import sparse_net.py:6-11 performs)
+
+    assert hasattr(sp, "SparseConvTensor") and hasattr(sp, "SparseSequential") and hasattr(sp, "SparseModule")
+    from efg.modeling.operators import BoxAttnFunction  # noqa: F401  (VD/modules/box_attention.py:7)
+    from efg._C import box_attn_forward, hard_voxelize  # noqa: F401
+    from torch._six import string_classes  # noqa: F401
+
+    for n in names:
+        sys.modules.pop(n, None)
+    sys.modules.pop("efg", None)
+    sys.modules.pop("efg.modeling", None)

@@ -1,0 +1,105 @@
+"""GPU parity: tensor-core (tcgen05) sparse convolution vs the fp32 CPU oracle.
+
+Tolerances (stated per north_star "within 1e-3 fp32"): outputs here are O(1) (unit-variance inputs,
+weights scaled by 1/sqrt(fan_in)); 3xTF32 ("fp32x3", the default) must be within 2e-4 absolute (measured ~6e-5 at K = 1728: the tensor core's
+fp32 accumulator truncates, so 216 accumulation steps drift ~2^-14),
+single-pass TF32 within 5e-3."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sparse_conv as sc
+
+pytestmark = pytest.mark.gpu
+
+
+def _sites(rng, batch, dhw, m):
+    cells = np.sort(rng.choice(batch * dhw[0] * dhw[1] * dhw[2], size=m, replace=False))
+    d, h, w = dhw
+    return np.stack([cells // (d * h * w), (cells // (h * w)) % d, (cells // w) % h, cells % w], 1).astype(np.int32)
+
+
+@pytest.fixture
+def precision():
+    from efg_b200 import ops
+
+    old = ops.CONV_PRECISION
+    yield ops
+    ops.CONV_PRECISION = old
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32x3", 2e-4), ("tf32", 5e-3)])
+@pytest.mark.parametrize("cin,cout,m", [(16, 16, 3000), (16, 32, 1000), (32, 64, 2500), (64, 64, 127), (64, 128, 129),
+                                        (128, 128, 2000), (256, 256, 700), (32, 16, 1500), (64, 32, 40000)])
+def test_tc_forward_vs_oracle(precision, mode, tol, cin, cout, m):
+    ops = precision
+    ops.CONV_PRECISION = mode
+    rng = np.random.default_rng(cin + cout + m)
+    torch.manual_seed(cin * 7 + cout)
+    batch, dhw = 2, [12, 64, 64]
+    coords = _sites(rng, batch, dhw, m)
+    feats = torch.randn(m, cin)
+    w = torch.randn(cout, 27, cin) / np.sqrt(27 * cin * 0.5)
+    bias = torch.randn(cout)
+    nbr = sc.subm_rulebook(coords, batch, dhw, 3)
+    exp = sc.conv(feats, w.view(cout, 3, 3, 3, cin), bias, nbr)
+    assert ops.spconv_tc_supported(cin, cout, 27)
+    out = ops.spconv_tc(feats.cuda(), w.cuda(), bias.cuda(), torch.from_numpy(nbr).int().cuda(), 0)
+    err = (out.cpu() - exp).abs().max().item()
+    assert err < tol, (mode, cin, cout, m, err)
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32x3", 2e-4), ("tf32", 1e-2)])
+@pytest.mark.parametrize("cin,cout", [(16, 16), (32, 64), (128, 128)])
+@pytest.mark.parametrize("subm", [True, False])
+def test_tc_module_forward_backward_vs_oracle(precision, mode, tol, cin, cout, subm):
+    from efg_b200.spconv import SparseConv3d, SparseConvTensor, SubMConv3d
+
+    ops = precision
+    ops.CONV_PRECISION = mode
+    rng = np.random.default_rng(cin + cout)
+    torch.manual_seed(cin + 3 * cout)
+    batch, dhw = 2, [9, 40, 41]
+    m = 3000
+    coords = _sites(rng, batch, dhw, m)
+    feats = torch.randn(m, cin)
+    if subm:
+        mod = SubMConv3d(cin, cout, 3, padding=1, bias=True, indice_key="k")
+        nbr = sc.subm_rulebook(coords, batch, dhw, 3)
+    else:
+        mod = SparseConv3d(cin, cout, 3, 2, padding=1, bias=False)
+        _, _, nbr, _ = sc.sparse_rulebook(coords, batch, dhw, 3, 2, 1)
+    w = mod.weight.detach().clone().requires_grad_(True)
+    b = mod.bias.detach().clone().requires_grad_(True) if mod.bias is not None else None
+    fo = feats.clone().requires_grad_(True)
+    yo = sc.conv(fo, w, b, nbr)
+    go = torch.randn_like(yo)
+    yo.backward(go)
+    mod = mod.cuda()
+    fg = feats.cuda().requires_grad_(True)
+    x = SparseConvTensor(fg, torch.from_numpy(coords).cuda(), dhw, batch)
+    x._rows_sorted = True
+    y = mod(x)
+    assert (y.features.detach().cpu() - yo.detach()).abs().max().item() < tol
+    y.features.backward(go.cuda())
+    assert (fg.grad.cpu() - fo.grad).abs().max().item() < tol * 4
+    scale = max(1.0, float(w.grad.abs().max()))
+    assert (mod.weight.grad.cpu() - w.grad).abs().max().item() < 2e-4 * scale  # wgrad is the fp32 FFMA kernel
+
+
+def test_tc_zcollapse_and_k3_kernels(precision):
+    """(3,1,1)/(2,1,1) z-collapse conv of the backbone heads: 3 taps, 128 channels."""
+    from efg_b200.spconv import SparseConv3d, SparseConvTensor
+
+    ops = precision
+    ops.CONV_PRECISION = "fp32x3"
+    rng = np.random.default_rng(77)
+    batch, dhw = 2, [6, 47, 47]
+    coords = _sites(rng, batch, dhw, 4000)
+    feats = torch.randn(4000, 128)
+    mod = SparseConv3d(128, 128, (3, 1, 1), (2, 1, 1), padding=(1, 0, 0), bias=False)
+    oc, od, nbr, _ = sc.sparse_rulebook(coords, batch, dhw, (3, 1, 1), (2, 1, 1), (1, 0, 0))
+    exp = sc.conv(feats, mod.weight.detach(), None, nbr)
+    y = mod.cuda()(SparseConvTensor(feats.cuda(), torch.from_numpy(coords).cuda(), dhw, batch))
+    assert np.array_equal(y.indices.cpu().numpy(), oc)
+    assert (y.features.detach().cpu() - exp).abs().max().item() < 2e-4
