@@ -41,6 +41,8 @@ SIGNATURES = {
     "efgb_spconv_tc_packed_bytes": (_sz, [_int, _int, _int, _int]),
     "efgb_spconv_tc_pack": (_int, [_vp, _int, _int, _int, _int, _int, _vp, _vp]),
     "efgb_spconv_tc_forward": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp]),
+    "efgb_spconv_tc_wgrad_supported": (_int, [_int, _int, _int]),
+    "efgb_spconv_tc_wgrad": (_int, [_vp, _i64, _int, _vp, _vp, _i64, _int, _int, _int, _vp, _vp]),
     "efgb_spconv_wgrad": (_int, [_vp, _i64, _int, _vp, _vp, _i64, _int, _int, _vp, _vp]),
     "efgb_sparse_to_dense": (_int, [_vp, _vp, _i64, _int, _int, _host_i32x3, _vp, _vp]),
     "efgb_dense_to_sparse": (_int, [_vp, _vp, _i64, _int, _int, _host_i32x3, _vp, _vp]),

@@ -394,6 +394,298 @@ pack_weights_kernel(const float* __restrict__ w, int c_out, int taps, int c_in, 
   }
 }
 
+
+// ================================================================================================
+// wgrad on the tensor cores:  dW[(tap, ci), co] = sum over output rows  A[row, (tap, ci)] * G[row, co]
+//   A[row, (tap, ci)] = in[nbr[row, tap], ci]   (gathered, zeros where nbr = -1),  G = grad_out.
+// The reduction runs over ROWS, so both operands are "MN-major" for the tensor core: a stage holds
+// 32 rows; the 128-wide M slice (a group of 128 consecutive flattened (tap, ci) indices) and the N = Cout
+// columns are split into 32-float column blocks, each block stored as [32 rows][128 B] with the
+// 32-byte-base 128B swizzle that MN-major tf32 requires (atoms of 4 rows x 128 B, LBO = block stride,
+// SBO = 512 B between 4-row groups; one K = 8 MMA spans two atoms).
+// A work item = (M group, row chunk); persistent CTAs stride over items; the fp32 accumulator
+// [128 x Cout] lives in TMEM (double buffered) and is flushed with coalesced red.global.add into the
+// reference parameter layout dW[co][tap][ci].
+// ================================================================================================
+constexpr int kWgRows = 32;  // rows (K) per stage
+
+struct WgradParams {
+  const float* in;      // [num_in, c_in]
+  const float* gout;    // [num_out, c_out]
+  const int32_t* nbr;   // [num_out, taps]
+  float* dw;            // [c_out, taps, c_in], zero-initialised
+  int64_t num_out;
+  int c_in, c_out, taps, n_pad;
+  int groups;           // ceil(taps * c_in / 128)
+  int row_chunks;
+  int64_t rows_per_chunk;  // multiple of kWgRows
+  int num_items;
+};
+
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;   // SBO: 4 K-rows x 128 B per swizzle atom
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(1) << 61;          // SWIZZLE_128B_BASE32B
+  return d;
+}
+
+// Byte offset of 16-byte piece `pc` (0..7 within a 32-float column block) of K-row r inside a column block.
+// MN-major tf32 operands must use the 128B swizzle with a 32-byte base (cutlass sm100_common.inl:89-94,
+// Layout_MN_SW128_32B_Atom = Swizzle<2,5,2> over 4 rows x 128 B): the 32-byte chunk index is XORed with r & 3.
+__device__ __forceinline__ uint32_t mn_piece_offset(int r, int pc) {
+  return static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(((pc & 7) >> 1) ^ (r & 3)) << 5) +
+         (static_cast<uint32_t>(pc & 1) << 4);
+}
+
+template <bool kSplit>
+__global__ void __launch_bounds__(kThreads, 1) spconv_wgrad_tc_kernel(const WgradParams p, const int stages) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int kParts = kSplit ? 2 : 1;
+  const int a_part = 4 * kWgRows * 128;                 // 4 column blocks of the M slice
+  const int g_part = (p.n_pad / 32) * kWgRows * 128;    // n_pad/32 column blocks of grad_out
+  const int stage_bytes = kParts * (a_part + g_part);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + stages;
+  uint64_t* tmem_full = bars + 2 * stages;
+  uint64_t* tmem_empty = bars + 2 * stages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(2 * p.n_pad)) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), kProducerWarps);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tmem_full[a]), 1);
+      mbar_init(smem_u32(&tmem_empty[a]), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int flat_m = p.taps * p.c_in;
+
+  if (warp < kProducerWarps) {
+    // ================= producers: gather A rows and stream grad_out rows =================
+    int stage = 0;
+    uint32_t phase = 0;
+    const int tid = threadIdx.x;  // 0..255
+    const int pg = p.n_pad / 4;   // 16-byte pieces per grad_out row (padded)
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const int g = item % p.groups;
+      const int64_t row_begin = static_cast<int64_t>(item / p.groups) * p.rows_per_chunk;
+      int64_t row_end = row_begin + p.rows_per_chunk;
+      if (row_end > p.num_out) row_end = p.num_out;
+      for (int64_t rb = row_begin; rb < row_end; rb += kWgRows) {
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        uint8_t* a_hi = smem + static_cast<size_t>(stage) * stage_bytes;
+        uint8_t* a_lo = a_hi + a_part;
+        uint8_t* g_hi = a_hi + kParts * a_part;
+        uint8_t* g_lo = g_hi + g_part;
+        // ---- A: 32 rows x 32 pieces; one warp covers one row per pass
+        int32_t src[4];
+        int ci_of[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int e = i * 256 + tid;
+          const int r = e >> 5, pc = e & 31;
+          const int flat = g * 128 + pc * 4;
+          const int64_t row = rb + r;
+          src[i] = -1;
+          ci_of[i] = 0;
+          if (flat < flat_m && row < row_end) {
+            const int tap = flat / p.c_in;
+            ci_of[i] = flat - tap * p.c_in;
+            src[i] = __ldg(p.nbr + row * p.taps + tap);
+          }
+        }
+        float4 va[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (src[i] >= 0) va[i] = __ldg(reinterpret_cast<const float4*>(p.in + static_cast<int64_t>(src[i]) * p.c_in + ci_of[i]));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int e = i * 256 + tid;
+          const int r = e >> 5, pc = e & 31;
+          const uint32_t off = static_cast<uint32_t>(pc >> 3) * (kWgRows * 128) + mn_piece_offset(r, pc);
+          if (kSplit) {
+            float4 hi, lo;
+            hi.x = __uint_as_float(__float_as_uint(va[i].x) & 0xFFFFE000u);
+            hi.y = __uint_as_float(__float_as_uint(va[i].y) & 0xFFFFE000u);
+            hi.z = __uint_as_float(__float_as_uint(va[i].z) & 0xFFFFE000u);
+            hi.w = __uint_as_float(__float_as_uint(va[i].w) & 0xFFFFE000u);
+            lo.x = va[i].x - hi.x;
+            lo.y = va[i].y - hi.y;
+            lo.z = va[i].z - hi.z;
+            lo.w = va[i].w - hi.w;
+            *reinterpret_cast<float4*>(a_hi + off) = hi;
+            *reinterpret_cast<float4*>(a_lo + off) = lo;
+          } else {
+            *reinterpret_cast<float4*>(a_hi + off) = va[i];
+          }
+        }
+        // ---- G: 32 rows x pg pieces
+        for (int e0 = 0; e0 < kWgRows * pg; e0 += 256 * 4) {
+          float4 vg[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int e = e0 + i * 256 + tid;
+            vg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e < kWgRows * pg) {
+              const int r = e / pg, pc = e - r * pg;
+              const int64_t row = rb + r;
+              if (row < row_end && pc * 4 < p.c_out) vg[i] = __ldg(reinterpret_cast<const float4*>(p.gout + row * p.c_out + pc * 4));
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int e = e0 + i * 256 + tid;
+            if (e < kWgRows * pg) {
+              const int r = e / pg, pc = e - r * pg;
+              const uint32_t off = static_cast<uint32_t>(pc >> 3) * (kWgRows * 128) + mn_piece_offset(r, pc);
+              if (kSplit) {
+                float4 hi, lo;
+                hi.x = __uint_as_float(__float_as_uint(vg[i].x) & 0xFFFFE000u);
+                hi.y = __uint_as_float(__float_as_uint(vg[i].y) & 0xFFFFE000u);
+                hi.z = __uint_as_float(__float_as_uint(vg[i].z) & 0xFFFFE000u);
+                hi.w = __uint_as_float(__float_as_uint(vg[i].w) & 0xFFFFE000u);
+                lo.x = vg[i].x - hi.x;
+                lo.y = vg[i].y - hi.y;
+                lo.z = vg[i].z - hi.z;
+                lo.w = vg[i].w - hi.w;
+                *reinterpret_cast<float4*>(g_hi + off) = hi;
+                *reinterpret_cast<float4*>(g_lo + off) = lo;
+              } else {
+                *reinterpret_cast<float4*>(g_hi + off) = vg[i];
+              }
+            }
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase[2] = {0, 0};
+      // both operands MN-major: bits 15 and 16
+      const uint32_t idesc = make_idesc_tf32(kTileM, p.n_pad) | (1u << 15) | (1u << 16);
+      const uint32_t blk = kWgRows * 128;  // column-block stride
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const int64_t row_begin = static_cast<int64_t>(item / p.groups) * p.rows_per_chunk;
+        int64_t row_end = row_begin + p.rows_per_chunk;
+        if (row_end > p.num_out) row_end = p.num_out;
+        mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase[acc] ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * p.n_pad);
+        uint32_t first = 1;
+        for (int64_t rb = row_begin; rb < row_end; rb += kWgRows) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t a_lo = a_hi + a_part;
+          const uint32_t g_hi = a_hi + kParts * a_part;
+          const uint32_t g_lo = g_hi + g_part;
+#pragma unroll
+          for (int ks = 0; ks < kWgRows / 8; ++ks) {
+            const uint32_t o = ks * 1024;  // 8 rows x 128 B inside every column block
+            if (kSplit) {
+              tc_mma_tf32(tmem_d, make_desc_mn_sw128(a_lo + o, blk), make_desc_mn_sw128(g_hi + o, blk), idesc, first ? 0u : 1u);
+              tc_mma_tf32(tmem_d, make_desc_mn_sw128(a_hi + o, blk), make_desc_mn_sw128(g_lo + o, blk), idesc, 1u);
+              tc_mma_tf32(tmem_d, make_desc_mn_sw128(a_hi + o, blk), make_desc_mn_sw128(g_hi + o, blk), idesc, 1u);
+            } else {
+              tc_mma_tf32(tmem_d, make_desc_mn_sw128(a_hi + o, blk), make_desc_mn_sw128(g_hi + o, blk), idesc, first ? 0u : 1u);
+            }
+            first = 0;
+          }
+          tc_commit(smem_u32(&empty_bar[stage]));
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(smem_u32(&tmem_full[acc]));
+        acc_phase[acc] ^= 1;
+        acc ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= kLoaderWarp + 1) {
+    // ================= epilogue: TMEM -> red.global.add into dW[co][tap][ci] =================
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase[2] = {0, 0};
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const int g = item % p.groups;
+      const int64_t row_begin = static_cast<int64_t>(item / p.groups) * p.rows_per_chunk;
+      mbar_wait(smem_u32(&tmem_full[acc]), acc_phase[acc]);
+      tc_fence_after();
+      const int flat = g * 128 + quarter * 32 + lane;
+      const int tap = flat / p.c_in;
+      const int ci = flat - tap * p.c_in;
+      const bool m_ok = flat < flat_m && row_begin < p.num_out;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * p.n_pad);
+      for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+        uint32_t r[16];
+        tc_ld16(taddr + c0, r);
+        tc_wait_ld();
+        if (m_ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int co = c0 + j;
+            const float v = __uint_as_float(r[j]);
+            if (co < p.c_out && v != 0.f) atomicAdd(p.dw + (static_cast<int64_t>(co) * p.taps + tap) * p.c_in + ci, v);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
+      acc_phase[acc] ^= 1;
+      acc ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+static bool wgrad_supported(int c_in, int c_out, int taps) {
+  const bool cin_ok = c_in >= 16 && c_in % 4 == 0 && ((128 % c_in == 0) || (c_in % 128 == 0));
+  return cin_ok && c_out >= 16 && c_out <= 256 && c_out % 16 == 0 && taps >= 1 && taps <= kMaxTaps;
+}
+
 static bool supported(int c_red, int n_out, int taps) {
   return c_red >= 4 && c_red % 4 == 0 && n_out >= 16 && n_out <= 256 && n_out % 16 == 0 && taps >= 1 && taps <= kMaxTaps;
 }
@@ -477,5 +769,65 @@ extern "C" int efgb_spconv_tc_forward(const float* in_feats, int64_t num_in, int
     tc::spconv_tc_kernel<false><<<grid, tc::kThreads, smem, stream>>>(p, stages);
   }
   EFGB_LAUNCH_OK("spconv_tc_kernel");
+  return EFGB_OK;
+}
+
+extern "C" int efgb_spconv_tc_wgrad_supported(int c_in, int c_out, int taps) { return tc::wgrad_supported(c_in, c_out, taps) ? 1 : 0; }
+
+extern "C" int efgb_spconv_tc_wgrad(const float* in_feats, int64_t num_in, int c_in, const float* grad_out,
+                                    const int32_t* nbr, int64_t num_out, int taps, int c_out, int split, float* dw_param,
+                                    efgb_stream_t stream_) {
+  cudaStream_t stream = as_stream(stream_);
+  EFGB_REQUIRE(tc::wgrad_supported(c_in, c_out, taps), EFGB_EINVAL, "spconv_tc_wgrad: unsupported shape (c_in=%d c_out=%d taps=%d)",
+               c_in, c_out, taps);
+  EFGB_REQUIRE(num_in >= 0 && num_out >= 0 && dw_param, EFGB_EINVAL, "spconv_tc_wgrad: bad argument");
+  EFGB_CUDA_OK(cudaMemsetAsync(dw_param, 0, static_cast<size_t>(c_out) * taps * c_in * sizeof(float), stream));
+  if (num_out == 0 || num_in == 0) return EFGB_OK;
+  EFGB_REQUIRE(in_feats && grad_out && nbr, EFGB_EINVAL, "spconv_tc_wgrad: null pointer");
+  EFGB_REQUIRE((reinterpret_cast<uintptr_t>(in_feats) & 15) == 0 && (reinterpret_cast<uintptr_t>(grad_out) & 15) == 0, EFGB_EINVAL,
+               "spconv_tc_wgrad: feature pointers must be 16-byte aligned");
+  tc::WgradParams p;
+  p.in = in_feats;
+  p.gout = grad_out;
+  p.nbr = nbr;
+  p.dw = dw_param;
+  p.num_out = num_out;
+  p.c_in = c_in;
+  p.c_out = c_out;
+  p.taps = taps;
+  p.n_pad = c_out < 32 ? 32 : (c_out + 31) / 32 * 32;
+  p.groups = (taps * c_in + 127) / 128;
+  int64_t chunks = (kNumSMs * 3 + p.groups - 1) / p.groups;
+  const int64_t max_chunks = (num_out + 255) / 256;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  int64_t rows = (num_out + chunks - 1) / chunks;
+  rows = (rows + tc::kWgRows - 1) / tc::kWgRows * tc::kWgRows;
+  p.rows_per_chunk = rows;
+  p.row_chunks = static_cast<int>((num_out + rows - 1) / rows);
+  p.num_items = p.groups * p.row_chunks;
+  const int parts = split ? 2 : 1;
+  const int stage_bytes = parts * (4 * tc::kWgRows * 128 + (p.n_pad / 32) * tc::kWgRows * 128);
+  int stages = (227 * 1024 - 4096) / stage_bytes;
+  if (stages > 6) stages = 6;
+  EFGB_REQUIRE(stages >= 2, EFGB_EINVAL, "spconv_tc_wgrad: tile does not fit shared memory");
+  const size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + (2 * stages + 4) * 8 + 16;
+  const int grid = p.num_items < kNumSMs ? p.num_items : kNumSMs;
+  if (split) {
+    static bool configured = false;
+    if (!configured) {
+      EFGB_CUDA_OK(cudaFuncSetAttribute(tc::spconv_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      configured = true;
+    }
+    tc::spconv_wgrad_tc_kernel<true><<<grid, tc::kThreads, smem, stream>>>(p, stages);
+  } else {
+    static bool configured = false;
+    if (!configured) {
+      EFGB_CUDA_OK(cudaFuncSetAttribute(tc::spconv_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      configured = true;
+    }
+    tc::spconv_wgrad_tc_kernel<false><<<grid, tc::kThreads, smem, stream>>>(p, stages);
+  }
+  EFGB_LAUNCH_OK("spconv_wgrad_tc_kernel");
   return EFGB_OK;
 }

@@ -311,6 +311,29 @@ def spconv_tc(feats, w_param, bias, nbr, mode):
     return out
 
 
+def spconv_tc_wgrad_supported(c_in, c_out, taps):
+    return CONV_PRECISION != "simt" and bool(_lib.lib().efgb_spconv_tc_wgrad_supported(c_in, c_out, taps))
+
+
+def spconv_tc_wgrad(feats, grad_out, nbr, taps, c_in, c_out):
+    """Tensor-core wgrad; returns dW in the reference parameter layout [c_out, taps, c_in]."""
+    _check(feats, "features", torch.float32)
+    _check(grad_out, "grad_out", torch.float32)
+    _check(nbr, "rulebook", torch.int32)
+    dw = torch.empty((c_out, taps, c_in), dtype=torch.float32, device=feats.device)
+    L = _lib.lib()
+    split = 1 if CONV_PRECISION == "fp32x3" else 0
+    t0 = PROFILER.begin() if PROFILER is not None else None
+    rc = L.efgb_spconv_tc_wgrad(_p(feats), feats.shape[0], c_in, _p(grad_out), _p(nbr), nbr.shape[0], taps, c_out, split,
+                                _p(dw), _stream())
+    _lib.check(rc, "spconv_tc_wgrad")
+    if t0 is not None:
+        m_out = nbr.shape[0]
+        nbytes = 4 * (feats.shape[0] * c_in + m_out * c_out + taps * c_in * c_out + taps * m_out)
+        PROFILER.end("spconv_tc_wgrad_c%d" % max(c_in, c_out), t0, nbytes, 2 * m_out * taps * c_in * c_out)
+    return dw
+
+
 def spconv_wgrad(feats, grad_out, nbr, taps, c_in, c_out):
     _check(feats, "features", torch.float32)
     _check(grad_out, "grad_out", torch.float32)

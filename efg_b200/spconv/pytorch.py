@@ -132,7 +132,10 @@ class _SparseConvFn(Function):
                     w_t = w_t.flip(0)
                 d_feat = ops.spconv_forward(grad_out, w_t.contiguous(), None, table)
         if ctx.needs_input_grad[1]:
-            d_w = ops.spconv_wgrad(features, grad_out, rb.nbr, taps, c_in, c_out).permute(2, 0, 1).contiguous()
+            if ops.spconv_tc_wgrad_supported(c_in, c_out, taps):
+                d_w = ops.spconv_tc_wgrad(features, grad_out, rb.nbr, taps, c_in, c_out)
+            else:
+                d_w = ops.spconv_wgrad(features, grad_out, rb.nbr, taps, c_in, c_out).permute(2, 0, 1).contiguous()
         if ctx.has_bias and ctx.needs_input_grad[2]:
             d_b = grad_out.sum(0)
         return d_feat, d_w, d_b, None

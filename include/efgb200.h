@@ -169,6 +169,15 @@ int efgb_spconv_tc_forward(const float* in_feats, int64_t num_in, int c_red, con
                            int64_t num_out, int taps, int n_out, int split, float* out_feats,
                            efgb_stream_t stream);
 
+/* Tensor-core wgrad: dw_param[co, tap, ci] = sum_o in[nbr[o,tap], ci] * grad_out[o, co], written in the
+ * reference parameter layout [c_out, taps, c_in] (zero-filled by the callee, accumulated with
+ * red.global.add).  Supported when c_in divides 128 or is a multiple of 128 (>= 16) and c_out % 16 == 0,
+ * c_out <= 256. */
+int efgb_spconv_tc_wgrad_supported(int c_in, int c_out, int taps);
+int efgb_spconv_tc_wgrad(const float* in_feats, int64_t num_in, int c_in, const float* grad_out,
+                         const int32_t* nbr, int64_t num_out, int taps, int c_out, int split,
+                         float* dw_param, efgb_stream_t stream);
+
 /* dw[k, ci, co] = sum_o in[nbr[o,k], ci] * grad_out[o, co]; dw is zero-filled by the callee. */
 int efgb_spconv_wgrad(const float* in_feats, int64_t num_in, int c_in,
                       const float* grad_out, const int32_t* nbr, int64_t num_out, int num_taps,
