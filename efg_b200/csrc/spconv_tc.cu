@@ -8,7 +8,8 @@
 // K is consumed in chunks of 32 floats = one 128-byte swizzled row per operand row.
 //
 // Roles inside one persistent CTA (one CTA per SM, tiles strided over the grid):
-//   warps 0-7   A producers: 8 lanes gather one 128-byte row piece with coalesced LDG.128, split it
+//   warps 0-7   A producers (four warp pairs, each owning every 4th K chunk): 8 lanes gather one 128-byte
+//               row piece with coalesced LDG.128 (16 independent loads in flight per thread), split it
 //               into tf32 hi/lo parts, and store it swizzled into the stage's A tiles
 //   warp  8     MMA issuer: one elected lane issues tcgen05.mma.kind::tf32 (M=128, N, K=8) into TMEM;
 //               tcgen05.commit releases the stage / publishes the accumulator
@@ -19,6 +20,8 @@
 // Precision: kSplit = true runs the 3xTF32 scheme (a = a_hi + a_lo, b = b_hi + b_lo;
 // a_hi*b_hi + a_lo*b_hi + a_hi*b_lo with fp32 accumulation), error ~2^-21 relative, i.e. fp32-faithful
 // (the reference runs this path in fp32).  kSplit = false is single-pass TF32.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace efgb {
@@ -117,6 +120,8 @@ struct Params {
   int64_t num_out;
   int c_red, taps, n_out, chunks;
   int num_tiles;
+  int n_cta;             // output columns per CTA (n_out / gridDim.y)
+  int debug;             // perf experiments only: 1 = no MMAs, 2 = no gather loads, 4 = no index loads
 };
 
 template <bool kSplit>
@@ -134,17 +139,87 @@ __host__ inline int pick_stages(int stage_bytes, int nbr_bytes) {
   return s;
 }
 
+// A producers.  kGroups warp groups; group g owns every kGroups-th K chunk of this CTA's chunk stream, so
+// kGroups chunks are gathered concurrently and every thread keeps 1024/(threads per group) independent
+// 16-byte loads in flight (the gather is latency-bound otherwise).  The rulebook entry is read straight
+// from global memory (8 lanes share one entry -> broadcast); the smem slot is only waited for AFTER the
+// loads were issued.  kGroups must not exceed the number of stages: a group that is a full ring ahead of
+// the MMA would otherwise see an aliased mbarrier parity.
+template <bool kSplit, int kGroups>
+__device__ __forceinline__ void produce_a(const Params& p, const int stages, uint8_t* stage_base, const int stage_bytes,
+                                          uint64_t* full_bar, uint64_t* empty_bar, const int warp, const int lane) {
+  constexpr int kWarpsPerGroup = kProducerWarps / kGroups;
+  constexpr int kPieces = (kTileM * 8) / (kWarpsPerGroup * 32);  // 16-byte pieces per thread per chunk
+  const int a_part = kTileM * 128;
+  const int gidx = warp / kWarpsPerGroup;
+  const int gw = warp % kWarpsPerGroup;
+  const int row_in_group = lane >> 3;  // 0..3
+  const int q = lane & 7;              // 16-byte piece of the 128-byte row
+  const int my_tiles = (p.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int64_t total_chunks = static_cast<int64_t>(my_tiles) * p.chunks;
+  for (int64_t gc = gidx; gc < total_chunks; gc += kGroups) {
+    const int ti = static_cast<int>(gc / p.chunks);
+    const int c = static_cast<int>(gc - static_cast<int64_t>(ti) * p.chunks);
+    const int stage = static_cast<int>(gc % stages);
+    const uint32_t phase = static_cast<uint32_t>((gc / stages) & 1);
+    const int64_t r0 = (static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(ti) * gridDim.x) * kTileM;
+    const int kk = c * kChunkK + q * 4;  // first K index of this lane's 16-byte piece
+    const int tap = kk / p.c_red;
+    const int ci = kk - tap * p.c_red;
+    const bool tap_ok = tap < p.taps;
+    int32_t src[kPieces];
+#pragma unroll
+    for (int i = 0; i < kPieces; ++i) {
+      const int64_t row = r0 + (i * kWarpsPerGroup + gw) * 4 + row_in_group;
+      src[i] = (tap_ok && row < p.num_out && !(p.debug & 4)) ? __ldg(p.nbr + row * p.taps + tap) : -1;
+    }
+    float4 v[kPieces];
+#pragma unroll
+    for (int i = 0; i < kPieces; ++i) {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (src[i] >= 0 && !(p.debug & 2)) v[i] = __ldg(reinterpret_cast<const float4*>(p.in + static_cast<int64_t>(src[i]) * p.c_red + ci));
+    }
+    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+    uint8_t* a_hi = stage_base + static_cast<size_t>(stage) * stage_bytes;
+    uint8_t* a_lo = a_hi + a_part;
+#pragma unroll
+    for (int i = 0; i < kPieces; ++i) {
+      const int r = (i * kWarpsPerGroup + gw) * 4 + row_in_group;
+      const uint32_t off = static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(q ^ (r & 7)) << 4);
+      if (kSplit) {
+        float4 hi, lo;
+        hi.x = __uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u);
+        hi.y = __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u);
+        hi.z = __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u);
+        hi.w = __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u);
+        lo.x = v[i].x - hi.x;
+        lo.y = v[i].y - hi.y;
+        lo.z = v[i].z - hi.z;
+        lo.w = v[i].w - hi.w;
+        *reinterpret_cast<float4*>(a_hi + off) = hi;
+        *reinterpret_cast<float4*>(a_lo + off) = lo;
+      } else {
+        *reinterpret_cast<float4*>(a_hi + off) = v[i];
+      }
+    }
+    fence_proxy_async();  // make the generic-proxy stores visible to the tensor core (async proxy)
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
+  }
+}
+
 template <bool kSplit>
 __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p, const int stages) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the swizzle atoms
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int stage_bytes = Smem<kSplit>::stage_bytes(p.n_out);
+  const int n_cta = p.n_cta;                       // output columns owned by this CTA (N split over grid.y)
+  const int n0 = static_cast<int>(blockIdx.y) * n_cta;
+  const int stage_bytes = Smem<kSplit>::stage_bytes(n_cta);
   const int a_part = kTileM * 128;
-  const int b_part = p.n_out * 128;
+  const int b_part = n_cta * 128;
   uint8_t* stage_base = smem;
-  int32_t* s_nbr = reinterpret_cast<int32_t*>(smem + static_cast<size_t>(stages) * stage_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_nbr) + ((kTileM * p.taps * 4 + 15) & ~15));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * stage_bytes);
   // bars: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then the TMEM base word
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + stages;
@@ -154,14 +229,15 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p, 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int groups = stages >= 4 ? 4 : 2;  // producer warp groups (never more than stages)
 
   // TMEM columns: two accumulators of n_out fp32 columns, power of two >= 32
   uint32_t tmem_cols = 32;
-  while (tmem_cols < static_cast<uint32_t>(2 * p.n_out)) tmem_cols <<= 1;
+  while (tmem_cols < static_cast<uint32_t>(2 * n_cta)) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), kProducerWarps + 1);
+      mbar_init(smem_u32(&full_bar[s]), kProducerWarps / groups + 1);  // one producer warp group + the weight loader
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -182,83 +258,31 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p, 
 
   if (warp < kProducerWarps) {
     // ================= A producers =================
-    int stage = 0;
-    uint32_t phase = 0;
-    const int row_in_group = lane >> 3;  // 0..3
-    const int q = lane & 7;              // 16-byte piece of the 128-byte row
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int64_t r0 = static_cast<int64_t>(tile) * kTileM;
-      // stage the tile's slice of the rulebook (producer warps only: named barrier 1)
-      asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory");
-      {
-        const int total = kTileM * p.taps;
-        const int64_t limit = (p.num_out - r0) * p.taps;
-        const int32_t* src = p.nbr + r0 * p.taps;
-        for (int e = threadIdx.x; e < total; e += kProducerWarps * 32) s_nbr[e] = e < limit ? src[e] : -1;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory");
-
-      for (int c = 0; c < p.chunks; ++c) {
-        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-        uint8_t* a_hi = stage_base + static_cast<size_t>(stage) * stage_bytes;
-        uint8_t* a_lo = a_hi + a_part;
-        const int kk = c * kChunkK + q * 4;  // first K index of this lane's 16-byte piece
-        const int tap = kk / p.c_red;
-        const int ci = kk - tap * p.c_red;
-        const bool tap_ok = tap < p.taps;
-        float4 v[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = (i * kProducerWarps + warp) * 4 + row_in_group;
-          const int32_t src = tap_ok ? s_nbr[r * p.taps + tap] : -1;
-          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (src >= 0) v[i] = __ldg(reinterpret_cast<const float4*>(p.in + static_cast<int64_t>(src) * p.c_red + ci));
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = (i * kProducerWarps + warp) * 4 + row_in_group;
-          const uint32_t off = static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(q ^ (r & 7)) << 4);
-          if (kSplit) {
-            float4 hi, lo;
-            hi.x = __uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u);
-            hi.y = __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u);
-            hi.z = __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u);
-            hi.w = __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u);
-            lo.x = v[i].x - hi.x;
-            lo.y = v[i].y - hi.y;
-            lo.z = v[i].z - hi.z;
-            lo.w = v[i].w - hi.w;
-            *reinterpret_cast<float4*>(a_hi + off) = hi;
-            *reinterpret_cast<float4*>(a_lo + off) = lo;
-          } else {
-            *reinterpret_cast<float4*>(a_hi + off) = v[i];
-          }
-        }
-        fence_proxy_async();  // make the generic-proxy stores visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
-        if (++stage == stages) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-    }
+    if (groups == 4)
+      produce_a<kSplit, 4>(p, stages, stage_base, stage_bytes, full_bar, empty_bar, warp, lane);
+    else
+      produce_a<kSplit, 2>(p, stages, stage_base, stage_bytes, full_bar, empty_bar, warp, lane);
   } else if (warp == kLoaderWarp) {
     // ================= B loader (TMA bulk copies of the packed weight chunks) =================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t b_bytes = static_cast<uint32_t>(Smem<kSplit>::b_bytes(p.n_out));
+      constexpr int kParts = Smem<kSplit>::kParts;
+      const uint32_t b_bytes = static_cast<uint32_t>(Smem<kSplit>::b_bytes(n_cta));
+      const uint32_t part_bytes = static_cast<uint32_t>(n_cta) * 128u;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         for (int c = 0; c < p.chunks; ++c) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t bar = smem_u32(&full_bar[stage]);
           mbar_arrive_expect_tx(bar, b_bytes);
           const uint32_t dst = smem_u32(stage_base + static_cast<size_t>(stage) * stage_bytes + Smem<kSplit>::a_bytes());
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.packed) + static_cast<size_t>(c) * b_bytes;
-          for (uint32_t o = 0; o < b_bytes; o += 16384u) {
-            const uint32_t n = b_bytes - o < 16384u ? b_bytes - o : 16384u;
-            bulk_g2s(dst + o, src + o, n, bar);
+          for (int part = 0; part < kParts; ++part) {
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.packed) +
+                                 (static_cast<size_t>(c * kParts + part) * p.n_out + n0) * 128u;
+            for (uint32_t o = 0; o < part_bytes; o += 16384u) {
+              const uint32_t n = part_bytes - o < 16384u ? part_bytes - o : 16384u;
+              bulk_g2s(dst + part * part_bytes + o, src + o, n, bar);
+            }
           }
           if (++stage == stages) {
             stage = 0;
@@ -275,11 +299,11 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p, 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase[2] = {0, 0};
-      const uint32_t idesc = make_idesc_tf32(kTileM, p.n_out);
+      const uint32_t idesc = make_idesc_tf32(kTileM, n_cta);
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase[acc] ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * p.n_out);
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * n_cta);
         for (int c = 0; c < p.chunks; ++c) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
@@ -291,6 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p, 
           const uint64_t db_lo = make_desc_sw128(b_hi + b_part);
 #pragma unroll
           for (int j = 0; j < kChunkK / 8; ++j) {
+            if (p.debug & 1) break;
             const uint64_t adv = static_cast<uint64_t>(j * 2);  // 8 tf32 = 32 bytes = 2 x 16 B
             if (kSplit) {
               tc_mma_tf32(tmem_d, da_lo + adv, db_hi + adv, idesc, (c | j) ? 1u : 0u);
@@ -321,20 +346,20 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p, 
       mbar_wait(smem_u32(&tmem_full[acc]), acc_phase[acc]);
       tc_fence_after();
       const int64_t row = static_cast<int64_t>(tile) * kTileM + quarter * 32 + lane;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * p.n_out);
-      for (int c0 = 0; c0 < p.n_out; c0 += 16) {
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * n_cta);
+      for (int c0 = 0; c0 < n_cta; c0 += 16) {
         uint32_t r[16];
         tc_ld16(taddr + c0, r);
         tc_wait_ld();
         if (row < p.num_out) {
-          float* dst = p.out + row * p.n_out + c0;
+          float* dst = p.out + row * p.n_out + n0 + c0;
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             float4 o;
-            o.x = __uint_as_float(r[j + 0]) + (p.bias ? p.bias[c0 + j + 0] : 0.f);
-            o.y = __uint_as_float(r[j + 1]) + (p.bias ? p.bias[c0 + j + 1] : 0.f);
-            o.z = __uint_as_float(r[j + 2]) + (p.bias ? p.bias[c0 + j + 2] : 0.f);
-            o.w = __uint_as_float(r[j + 3]) + (p.bias ? p.bias[c0 + j + 3] : 0.f);
+            o.x = __uint_as_float(r[j + 0]) + (p.bias ? p.bias[n0 + c0 + j + 0] : 0.f);
+            o.y = __uint_as_float(r[j + 1]) + (p.bias ? p.bias[n0 + c0 + j + 1] : 0.f);
+            o.z = __uint_as_float(r[j + 2]) + (p.bias ? p.bias[n0 + c0 + j + 2] : 0.f);
+            o.w = __uint_as_float(r[j + 3]) + (p.bias ? p.bias[n0 + c0 + j + 3] : 0.f);
             *reinterpret_cast<float4*>(dst + j) = o;
           }
         }
@@ -440,6 +465,115 @@ __device__ __forceinline__ uint32_t mn_piece_offset(int r, int pc) {
          (static_cast<uint32_t>(pc & 1) << 4);
 }
 
+__device__ __forceinline__ void split_store(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, const float4& v, bool split) {
+  if (split) {
+    float4 hi, lo;
+    hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+    hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+    hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+    hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    lo.x = v.x - hi.x;
+    lo.y = v.y - hi.y;
+    lo.z = v.z - hi.z;
+    lo.w = v.w - hi.w;
+    *reinterpret_cast<float4*>(hi_base + off) = hi;
+    *reinterpret_cast<float4*>(lo_base + off) = lo;
+  } else {
+    *reinterpret_cast<float4*>(hi_base + off) = v;
+  }
+}
+
+// wgrad producers: kGroups warp groups, group g owns every kGroups-th 32-row stage of this CTA's stage
+// stream (every work item has exactly rows_per_chunk/32 stage slots; slots past the end are zero tiles).
+template <bool kSplit, int kGroups>
+__device__ __forceinline__ void wgrad_produce(const WgradParams& p, const int stages, uint8_t* smem, const int stage_bytes,
+                                              const int a_part, const int g_part, uint64_t* full_bar, uint64_t* empty_bar,
+                                              const int warp, const int lane) {
+  constexpr int kParts = kSplit ? 2 : 1;
+  constexpr int kWarpsPerGroup = kProducerWarps / kGroups;
+  constexpr int kGroupThreads = kWarpsPerGroup * 32;
+  constexpr int kPiecesA = (kWgRows * 32) / kGroupThreads;  // 16-byte pieces of the A tile per thread
+  const int gidx = warp / kWarpsPerGroup;
+  const int tg = (warp % kWarpsPerGroup) * 32 + lane;
+  const int pg = p.n_pad / 4;  // 16-byte pieces per grad_out row (padded)
+  const int flat_m = p.taps * p.c_in;
+  const int spi = static_cast<int>(p.rows_per_chunk / kWgRows);  // stage slots per item
+  const int my_items = (p.num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int64_t total = static_cast<int64_t>(my_items) * spi;
+  for (int64_t gs = gidx; gs < total; gs += kGroups) {
+    const int it = static_cast<int>(gs / spi);
+    const int sl = static_cast<int>(gs - static_cast<int64_t>(it) * spi);
+    const int item = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+    const int g = item % p.groups;
+    const int64_t row_begin = static_cast<int64_t>(item / p.groups) * p.rows_per_chunk;
+    int64_t row_end = row_begin + p.rows_per_chunk;
+    if (row_end > p.num_out) row_end = p.num_out;
+    const int64_t rb = row_begin + static_cast<int64_t>(sl) * kWgRows;
+    const int stage = static_cast<int>(gs % stages);
+    const uint32_t phase = static_cast<uint32_t>((gs / stages) & 1);
+
+    // ---- A: 32 rows x 32 pieces
+    int32_t src[kPiecesA];
+    int ci_of[kPiecesA];
+#pragma unroll
+    for (int i = 0; i < kPiecesA; ++i) {
+      const int e = i * kGroupThreads + tg;
+      const int r = e >> 5, pc = e & 31;
+      const int flat = g * 128 + pc * 4;
+      const int64_t row = rb + r;
+      src[i] = -1;
+      ci_of[i] = 0;
+      if (flat < flat_m && row < row_end) {
+        const int tap = flat / p.c_in;
+        ci_of[i] = flat - tap * p.c_in;
+        src[i] = __ldg(p.nbr + row * p.taps + tap);
+      }
+    }
+    float4 va[kPiecesA];
+#pragma unroll
+    for (int i = 0; i < kPiecesA; ++i) {
+      va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (src[i] >= 0) va[i] = __ldg(reinterpret_cast<const float4*>(p.in + static_cast<int64_t>(src[i]) * p.c_in + ci_of[i]));
+    }
+    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+    uint8_t* a_hi = smem + static_cast<size_t>(stage) * stage_bytes;
+    uint8_t* a_lo = a_hi + a_part;
+    uint8_t* g_hi = a_hi + kParts * a_part;
+    uint8_t* g_lo = g_hi + g_part;
+#pragma unroll
+    for (int i = 0; i < kPiecesA; ++i) {
+      const int e = i * kGroupThreads + tg;
+      const int r = e >> 5, pc = e & 31;
+      split_store(a_hi, a_lo, static_cast<uint32_t>(pc >> 3) * (kWgRows * 128) + mn_piece_offset(r, pc), va[i], kSplit);
+    }
+    // ---- G: 32 rows x pg pieces, 8 per thread per pass
+    for (int e0 = 0; e0 < kWgRows * pg; e0 += kGroupThreads * 8) {
+      float4 vg[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int e = e0 + i * kGroupThreads + tg;
+        vg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < kWgRows * pg) {
+          const int r = e / pg, pc = e - r * pg;
+          const int64_t row = rb + r;
+          if (row < row_end && pc * 4 < p.c_out) vg[i] = __ldg(reinterpret_cast<const float4*>(p.gout + row * p.c_out + pc * 4));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int e = e0 + i * kGroupThreads + tg;
+        if (e < kWgRows * pg) {
+          const int r = e / pg, pc = e - r * pg;
+          split_store(g_hi, g_lo, static_cast<uint32_t>(pc >> 3) * (kWgRows * 128) + mn_piece_offset(r, pc), vg[i], kSplit);
+        }
+      }
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
+  }
+}
+
 template <bool kSplit>
 __global__ void __launch_bounds__(kThreads, 1) spconv_wgrad_tc_kernel(const WgradParams p, const int stages) {
   extern __shared__ uint8_t smem_raw[];
@@ -457,12 +591,13 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_wgrad_tc_kernel(const Wgra
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int pgroups = stages >= 4 ? 4 : 2;  // producer warp groups (never more than stages)
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(2 * p.n_pad)) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), kProducerWarps);
+      mbar_init(smem_u32(&full_bar[s]), kProducerWarps / pgroups);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -484,111 +619,10 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_wgrad_tc_kernel(const Wgra
 
   if (warp < kProducerWarps) {
     // ================= producers: gather A rows and stream grad_out rows =================
-    int stage = 0;
-    uint32_t phase = 0;
-    const int tid = threadIdx.x;  // 0..255
-    const int pg = p.n_pad / 4;   // 16-byte pieces per grad_out row (padded)
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const int g = item % p.groups;
-      const int64_t row_begin = static_cast<int64_t>(item / p.groups) * p.rows_per_chunk;
-      int64_t row_end = row_begin + p.rows_per_chunk;
-      if (row_end > p.num_out) row_end = p.num_out;
-      for (int64_t rb = row_begin; rb < row_end; rb += kWgRows) {
-        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-        uint8_t* a_hi = smem + static_cast<size_t>(stage) * stage_bytes;
-        uint8_t* a_lo = a_hi + a_part;
-        uint8_t* g_hi = a_hi + kParts * a_part;
-        uint8_t* g_lo = g_hi + g_part;
-        // ---- A: 32 rows x 32 pieces; one warp covers one row per pass
-        int32_t src[4];
-        int ci_of[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int e = i * 256 + tid;
-          const int r = e >> 5, pc = e & 31;
-          const int flat = g * 128 + pc * 4;
-          const int64_t row = rb + r;
-          src[i] = -1;
-          ci_of[i] = 0;
-          if (flat < flat_m && row < row_end) {
-            const int tap = flat / p.c_in;
-            ci_of[i] = flat - tap * p.c_in;
-            src[i] = __ldg(p.nbr + row * p.taps + tap);
-          }
-        }
-        float4 va[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (src[i] >= 0) va[i] = __ldg(reinterpret_cast<const float4*>(p.in + static_cast<int64_t>(src[i]) * p.c_in + ci_of[i]));
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int e = i * 256 + tid;
-          const int r = e >> 5, pc = e & 31;
-          const uint32_t off = static_cast<uint32_t>(pc >> 3) * (kWgRows * 128) + mn_piece_offset(r, pc);
-          if (kSplit) {
-            float4 hi, lo;
-            hi.x = __uint_as_float(__float_as_uint(va[i].x) & 0xFFFFE000u);
-            hi.y = __uint_as_float(__float_as_uint(va[i].y) & 0xFFFFE000u);
-            hi.z = __uint_as_float(__float_as_uint(va[i].z) & 0xFFFFE000u);
-            hi.w = __uint_as_float(__float_as_uint(va[i].w) & 0xFFFFE000u);
-            lo.x = va[i].x - hi.x;
-            lo.y = va[i].y - hi.y;
-            lo.z = va[i].z - hi.z;
-            lo.w = va[i].w - hi.w;
-            *reinterpret_cast<float4*>(a_hi + off) = hi;
-            *reinterpret_cast<float4*>(a_lo + off) = lo;
-          } else {
-            *reinterpret_cast<float4*>(a_hi + off) = va[i];
-          }
-        }
-        // ---- G: 32 rows x pg pieces
-        for (int e0 = 0; e0 < kWgRows * pg; e0 += 256 * 4) {
-          float4 vg[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int e = e0 + i * 256 + tid;
-            vg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e < kWgRows * pg) {
-              const int r = e / pg, pc = e - r * pg;
-              const int64_t row = rb + r;
-              if (row < row_end && pc * 4 < p.c_out) vg[i] = __ldg(reinterpret_cast<const float4*>(p.gout + row * p.c_out + pc * 4));
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int e = e0 + i * 256 + tid;
-            if (e < kWgRows * pg) {
-              const int r = e / pg, pc = e - r * pg;
-              const uint32_t off = static_cast<uint32_t>(pc >> 3) * (kWgRows * 128) + mn_piece_offset(r, pc);
-              if (kSplit) {
-                float4 hi, lo;
-                hi.x = __uint_as_float(__float_as_uint(vg[i].x) & 0xFFFFE000u);
-                hi.y = __uint_as_float(__float_as_uint(vg[i].y) & 0xFFFFE000u);
-                hi.z = __uint_as_float(__float_as_uint(vg[i].z) & 0xFFFFE000u);
-                hi.w = __uint_as_float(__float_as_uint(vg[i].w) & 0xFFFFE000u);
-                lo.x = vg[i].x - hi.x;
-                lo.y = vg[i].y - hi.y;
-                lo.z = vg[i].z - hi.z;
-                lo.w = vg[i].w - hi.w;
-                *reinterpret_cast<float4*>(g_hi + off) = hi;
-                *reinterpret_cast<float4*>(g_lo + off) = lo;
-              } else {
-                *reinterpret_cast<float4*>(g_hi + off) = vg[i];
-              }
-            }
-          }
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
-        if (++stage == stages) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-    }
+    if (pgroups == 4)
+      wgrad_produce<kSplit, 4>(p, stages, smem, stage_bytes, a_part, g_part, full_bar, empty_bar, warp, lane);
+    else
+      wgrad_produce<kSplit, 2>(p, stages, smem, stage_bytes, a_part, g_part, full_bar, empty_bar, warp, lane);
   } else if (warp == kMmaWarp) {
     if (lane == 0) {
       int stage = 0;
@@ -606,7 +640,8 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_wgrad_tc_kernel(const Wgra
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * p.n_pad);
         uint32_t first = 1;
-        for (int64_t rb = row_begin; rb < row_end; rb += kWgRows) {
+        (void)row_end;
+        for (int64_t rb = row_begin; rb < row_begin + p.rows_per_chunk; rb += kWgRows) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
@@ -747,12 +782,20 @@ extern "C" int efgb_spconv_tc_forward(const float* in_feats, int64_t num_in, int
   p.n_out = n_out;
   p.chunks = tc::chunks_for(taps, c_red);
   p.num_tiles = static_cast<int>((num_out + tc::kTileM - 1) / tc::kTileM);
-  const int nbr_bytes = (tc::kTileM * taps * 4 + 15) & ~15;
-  const int stage_bytes = split ? tc::Smem<true>::stage_bytes(n_out) : tc::Smem<false>::stage_bytes(n_out);
+  {
+    const char* dbg = getenv("EFGB_TC_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
+  const int nbr_bytes = 0;
+  // few tiles (deep levels): split the output channels over grid.y so that all SMs get work
+  int n_split = 1;
+  while (p.num_tiles * n_split * 2 <= kNumSMs && n_out / (n_split * 2) >= 32 && (n_out / (n_split * 2)) % 16 == 0) n_split *= 2;
+  p.n_cta = n_out / n_split;
+  const int stage_bytes = split ? tc::Smem<true>::stage_bytes(p.n_cta) : tc::Smem<false>::stage_bytes(p.n_cta);
   const int stages = tc::pick_stages(stage_bytes, nbr_bytes);
   EFGB_REQUIRE(stages >= 2, EFGB_EINVAL, "spconv_tc_forward: tile does not fit shared memory");
   const size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + nbr_bytes + (2 * stages + 4) * 8 + 16;
-  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  const dim3 grid(p.num_tiles * n_split < kNumSMs ? p.num_tiles : kNumSMs / n_split, n_split);
   if (split) {
     static bool configured = false;
     if (!configured) {

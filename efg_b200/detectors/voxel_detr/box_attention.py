@@ -61,14 +61,15 @@ class Box3dAttention(nn.Module):
         offset = F.linear(query, self.linear_box_weight, self.linear_box_bias)
         offset = offset.view(B, L, self.num_head, self.num_level, self.num_variable)
         ref = ref_windows.unsqueeze(2).unsqueeze(3) if ref_windows.dim() == 3 else ref_windows.unsqueeze(3)
-        ref_boxes = ref[..., [0, 1, 3, 4]]
-        ref_angles = ref[..., [6]]
+        ref_boxes = torch.cat((ref[..., 0:2], ref[..., 3:5]), dim=-1)  # (cx, cy, w, l); slices, no index upload
+        ref_angles = ref[..., 6:7]
         if self.with_rotation:
             offset, offset_angles = offset.split(4, dim=-1)
             angles = (ref_angles + offset_angles / 16) * 2 * math.pi
         else:
             angles = ref_angles.expand(B, L, self.num_head, self.num_level, 1)
-        boxes = ref_boxes + offset / 8 * ref_boxes[..., [2, 3, 2, 3]]
+        size = ref_boxes[..., 2:4]
+        boxes = ref_boxes + offset / 8 * torch.cat((size, size), dim=-1)
         center, size = boxes.unsqueeze(-2).split(2, dim=-1)
         cos, sin = torch.cos(angles), torch.sin(angles)
         rot = torch.stack([cos, -sin, sin, cos], dim=-1).view(B, L, self.num_head, self.num_level, 1, 2, 2)

@@ -8,16 +8,21 @@ def cxcyczlwh_to_corners(x):
     return torch.cat([c - 0.5 * s, c + 0.5 * s], dim=-1)
 
 
+def _vol(x):
+    """Product of the last-dim extents, written out: Tensor.prod's backward synchronises to look for zeros."""
+    return x[..., 0] * x[..., 1] * x[..., 2]
+
+
 def generalized_box3d_iou(a, b):
     """Axis-aligned 3-D GIoU between every pair: a [N,6], b [M,6] corner boxes -> [N,M]."""
     a = torch.nan_to_num(a)
     b = torch.nan_to_num(b)
-    vol_a = (a[:, 3:] - a[:, :3]).prod(-1)
-    vol_b = (b[:, 3:] - b[:, :3]).prod(-1)
-    inter = (torch.min(a[:, None, 3:], b[:, 3:]) - torch.max(a[:, None, :3], b[:, :3])).clamp(min=0).prod(-1)
+    vol_a = _vol(a[:, 3:] - a[:, :3])
+    vol_b = _vol(b[:, 3:] - b[:, :3])
+    inter = _vol((torch.min(a[:, None, 3:], b[:, 3:]) - torch.max(a[:, None, :3], b[:, :3])).clamp(min=0))
     union = vol_a[:, None] + vol_b - inter
     iou = inter / union
-    hull = (torch.max(a[:, None, 3:], b[:, 3:]) - torch.min(a[:, None, :3], b[:, :3])).clamp(min=0).prod(-1)
+    hull = _vol((torch.max(a[:, None, 3:], b[:, 3:]) - torch.min(a[:, None, :3], b[:, :3])).clamp(min=0))
     return iou - (hull - union) / hull
 
 
@@ -25,11 +30,11 @@ def generalized_box3d_iou_paired(a, b):
     """Same measure for matched pairs a[i] <-> b[i] ([N,6] each -> [N]); equals diag of the full matrix."""
     a = torch.nan_to_num(a)
     b = torch.nan_to_num(b)
-    vol_a = (a[:, 3:] - a[:, :3]).prod(-1)
-    vol_b = (b[:, 3:] - b[:, :3]).prod(-1)
-    inter = (torch.min(a[:, 3:], b[:, 3:]) - torch.max(a[:, :3], b[:, :3])).clamp(min=0).prod(-1)
+    vol_a = _vol(a[:, 3:] - a[:, :3])
+    vol_b = _vol(b[:, 3:] - b[:, :3])
+    inter = _vol((torch.min(a[:, 3:], b[:, 3:]) - torch.max(a[:, :3], b[:, :3])).clamp(min=0))
     union = vol_a + vol_b - inter
-    hull = (torch.max(a[:, 3:], b[:, 3:]) - torch.min(a[:, :3], b[:, :3])).clamp(min=0).prod(-1)
+    hull = _vol((torch.max(a[:, 3:], b[:, 3:]) - torch.min(a[:, :3], b[:, :3])).clamp(min=0))
     return inter / union - (hull - union) / hull
 
 

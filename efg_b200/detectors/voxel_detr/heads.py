@@ -61,8 +61,11 @@ class Det3DHead(nn.Module):
         boxes = (self.bbox_embed[layer_idx](embed) + inverse_sigmoid(anchors)).sigmoid()
         return logits, boxes
 
-    def compute_losses(self, outputs, targets, num_boxes=None):
-        loss_dict = self.losses(outputs, targets, num_boxes)
+    def compute_losses(self, outputs, targets, num_boxes=None, solved=None):
+        if solved is None:
+            loss_dict = self.losses(outputs, targets, num_boxes)
+        else:
+            loss_dict = self.losses.finish(outputs, targets, solved, num_boxes)
         weights = self.losses.weight_dict
         for k in list(loss_dict.keys()):
             if k in weights:

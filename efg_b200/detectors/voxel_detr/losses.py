@@ -20,6 +20,43 @@ def _src_idx(indices):
     return batch, src
 
 
+class TargetList(list):
+    """Per-scene target dicts plus their concatenation (``labels_cat`` [sum K], ``boxes_cat`` [sum K, 7],
+    ``offsets`` python ints), so that losses index ground truth with ONE device index tensor per layer."""
+
+    labels_cat = None
+    boxes_cat = None
+    offsets = None
+
+
+class MatchIndex:
+    """The Hungarian assignments of one output layer as device tensors: batch index, query index and the
+    index into the concatenated ground truth.  All layers of a step are uploaded in one pinned,
+    non-blocking copy (``upload_matches``) instead of one blocking copy per (layer, scene, loss)."""
+
+    def __init__(self, batch, src, tgt):
+        self.batch, self.src, self.tgt = batch, src, tgt
+
+
+def upload_matches(solved_layers, offsets, device):
+    """solved_layers: list (per layer) of lists (per scene) of (src_idx, tgt_idx) CPU int64 tensors."""
+    rows, sizes = [], []
+    for layer in solved_layers:
+        b = torch.cat([torch.full_like(src, i) for i, (src, _) in enumerate(layer)])
+        s_ = torch.cat([src for src, _ in layer])
+        t = torch.cat([tgt + offsets[i] for i, (_, tgt) in enumerate(layer)])
+        rows.append(torch.stack([b, s_, t]))
+        sizes.append(b.numel())
+    flat = torch.cat(rows, dim=1) if rows else torch.zeros((3, 0), dtype=torch.int64)
+    if device.type == "cuda":
+        flat = flat.pin_memory().to(device, non_blocking=True)
+    out, off = [], 0
+    for n in sizes:
+        out.append(MatchIndex(flat[0, off:off + n], flat[1, off:off + n], flat[2, off:off + n]))
+        off += n
+    return out
+
+
 class ClassificationLoss(nn.Module):
     def __init__(self, focal_alpha):
         super().__init__()
@@ -31,17 +68,22 @@ class ClassificationLoss(nn.Module):
         logits = outputs["pred_logits"]
         dev = logits.device
         onehot = torch.zeros_like(logits)
-        b_idx, s_idx = _src_idx(indices)
-        b_idx, s_idx = b_idx.to(dev), s_idx.to(dev)
-        tgt_cls = torch.cat([t["labels"][j.to(dev)] for t, (_, j) in zip(targets, indices)])
+        if isinstance(indices, MatchIndex):
+            b_idx, s_idx = indices.batch, indices.src
+            labels_cat = outputs.get("_labels_cat", targets.labels_cat)
+            tgt_cls = labels_cat[indices.tgt]
+        else:
+            b_idx, s_idx = _src_idx(indices)
+            b_idx, s_idx = b_idx.to(dev), s_idx.to(dev)
+            tgt_cls = torch.cat([t["labels"][j.to(dev)] for t, (_, j) in zip(targets, indices)])
         self.target_classes = tgt_cls
         if "topk_indexes" in outputs:
             topk = outputs["topk_indexes"]
             self.src_logits = torch.gather(logits, 1, topk.expand(-1, -1, logits.shape[-1]))[b_idx, s_idx]
-            onehot[b_idx, topk[b_idx, s_idx].squeeze(-1), tgt_cls] = 1
+            onehot.index_put_((b_idx, topk[b_idx, s_idx].squeeze(-1), tgt_cls), onehot.new_ones(()))
         else:
             self.src_logits = logits[b_idx, s_idx]
-            onehot[b_idx, s_idx, tgt_cls] = 1
+            onehot.index_put_((b_idx, s_idx, tgt_cls), onehot.new_ones(()))
         loss = sigmoid_focal_loss(logits, onehot, alpha=self.focal_alpha, gamma=2.0, reduction="sum") / num_boxes
         return {"loss_ce": loss}
 
@@ -50,11 +92,15 @@ class RegressionLoss(nn.Module):
     def forward(self, outputs, targets, indices, num_boxes):
         boxes = outputs["pred_boxes"]
         dev = boxes.device
-        b_idx, s_idx = _src_idx(indices)
-        b_idx, s_idx = b_idx.to(dev), s_idx.to(dev)
         if "topk_indexes" in outputs:
             boxes = torch.gather(boxes, 1, outputs["topk_indexes"].expand(-1, -1, boxes.shape[-1]))
-        tgt = torch.cat([t["gt_boxes"][j.to(dev)] for t, (_, j) in zip(targets, indices)], dim=0)
+        if isinstance(indices, MatchIndex):
+            b_idx, s_idx = indices.batch, indices.src
+            tgt = targets.boxes_cat[indices.tgt]
+        else:
+            b_idx, s_idx = _src_idx(indices)
+            b_idx, s_idx = b_idx.to(dev), s_idx.to(dev)
+            tgt = torch.cat([t["gt_boxes"][j.to(dev)] for t, (_, j) in zip(targets, indices)], dim=0)
         src_box, src_rad = boxes[b_idx, s_idx].split(6, dim=-1)
         tgt_box, tgt_rad = tgt.split(6, dim=-1)
         giou = generalized_box3d_iou_paired(cxcyczlwh_to_corners(src_box), cxcyczlwh_to_corners(tgt_box))
@@ -99,21 +145,35 @@ class Det3DLoss(nn.Module):
             n = float(t.item())
         return max(n / _world_size(), 1.0)
 
+    @staticmethod
+    def layers_of(outputs):
+        return list(outputs.get("aux_outputs", [])) + [{k: v for k, v in outputs.items() if k != "aux_outputs"}]
+
+    def prepare(self, outputs, targets):
+        """Cost matrices (device tensors) of every output layer, in layer-major, scene-minor order."""
+        mats = []
+        for lo in self.layers_of(outputs):
+            mats.extend(self.matcher.cost_matrices(lo, targets))
+        return mats
+
+    def finish(self, outputs, targets, solved, num_boxes):
+        """solved: per layer, either a MatchIndex (device) or a list of per-scene (src, tgt) CPU pairs."""
+        layers = self.layers_of(outputs)
+        losses = {}
+        for li, lo in enumerate(layers):
+            suffix = "" if li == len(layers) - 1 else "_{}".format(li)
+            if "_labels_cat" in outputs:
+                lo = dict(lo, _labels_cat=outputs["_labels_cat"])
+            for loss in self.losses:
+                for k, v in self.det3d_losses[loss](lo, targets, solved[li], num_boxes).items():
+                    losses[k + suffix] = v
+        return losses
+
     def forward(self, outputs, targets, num_boxes=None):
         if num_boxes is None:
             num_boxes = self.normaliser(targets, next(iter(outputs.values())).device)
-        layers = list(outputs.get("aux_outputs", [])) + [{k: v for k, v in outputs.items() if k != "aux_outputs"}]
         # all cost matrices first (GPU), one host transfer, then the assignments
-        mats = []
-        for lo in layers:
-            mats.extend(self.matcher.cost_matrices(lo, targets))
-        solved = self.matcher.solve(mats)
+        solved = self.matcher.solve(self.prepare(outputs, targets))
         bs = len(targets)
-        losses = {}
-        for li, lo in enumerate(layers):
-            indices = solved[li * bs:(li + 1) * bs]
-            suffix = "" if li == len(layers) - 1 else "_{}".format(li)
-            for loss in self.losses:
-                for k, v in self.det3d_losses[loss](lo, targets, indices, num_boxes).items():
-                    losses[k + suffix] = v
-        return losses
+        per_layer = [solved[i * bs:(i + 1) * bs] for i in range(len(solved) // max(bs, 1))]
+        return self.finish(outputs, targets, per_layer, num_boxes)

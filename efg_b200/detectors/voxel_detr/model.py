@@ -84,6 +84,7 @@ class VoxelDETR(nn.Module):
         self.transformer.decoder.detection_head = Det3DHead(config, with_aux=True, with_metrics=True,
                                                             num_classes=self.num_classes, num_layers=t.dec_layers)
         self.box_coder = VoxelBoxCoder3D(config.dataset.voxel_size, config.dataset.pc_range, device=self.device)
+        self._cpu_box_coder = VoxelBoxCoder3D(config.dataset.voxel_size, config.dataset.pc_range)
         grid = np.round((np.asarray(config.dataset.pc_range[3:], dtype=np.float32) -
                          np.asarray(config.dataset.pc_range[:3], dtype=np.float32)) /
                         np.asarray(config.dataset.voxel_size, dtype=np.float32)).astype(np.int64)
@@ -108,8 +109,10 @@ class VoxelDETR(nn.Module):
             pts.append(p.to(self.device, non_blocking=True))
             sizes.append(p.shape[0])
         points = torch.cat(pts, 0) if len(pts) > 1 else pts[0]
-        offs = torch.tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int32).to(self.device,
-                                                                                           non_blocking=True)
+        offs = torch.tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int32)
+        if self.device.type == "cuda":
+            offs = offs.pin_memory()
+        offs = offs.to(self.device, non_blocking=True)
         max_voxels = ds.get("max_voxel_num", 150000)
         if isinstance(max_voxels, (list, tuple)):
             max_voxels = max_voxels[0] if self.training else max_voxels[1]
@@ -120,12 +123,31 @@ class VoxelDETR(nn.Module):
         return r["mean"][:m], r["coors"][:m], r["num_points_per_voxel"][:m], self.grid_size
 
     def encode_targets(self, batched_inputs):
-        targets = []
+        """Ground truth of the batch -> normalised box codes (box_coder.encode) and 0-based labels.  The
+        encoding runs on the host copy (a few hundred boxes) and the batch is uploaded as TWO pinned,
+        non-blocking copies; per-scene dicts are views into the concatenation."""
+        from .losses import TargetList
+
+        cpu_coder = self._cpu_box_coder
+        enc = []
         for _, info in batched_inputs:
             ann = info["annotations"]
-            t = {k: torch.as_tensor(np.asarray(ann[k]), device=self.device)
-                 for k in ("gt_boxes", "difficulty", "num_points_in_gt", "labels") if k in ann}
-            targets.append(self.box_coder.encode(t))
+            t = {"gt_boxes": torch.as_tensor(np.asarray(ann["gt_boxes"], dtype=np.float32)),
+                 "labels": torch.as_tensor(np.asarray(ann["labels"], dtype=np.int64))}
+            enc.append(cpu_coder.encode(t))
+        sizes = [int(e["labels"].shape[0]) for e in enc]
+        boxes = torch.cat([e["gt_boxes"] for e in enc], 0) if enc else torch.zeros((0, 7))
+        labels = torch.cat([e["labels"] for e in enc], 0) if enc else torch.zeros((0,), dtype=torch.int64)
+        if self.device.type == "cuda":
+            boxes = boxes.pin_memory().to(self.device, non_blocking=True)
+            labels = labels.pin_memory().to(self.device, non_blocking=True)
+        targets = TargetList()
+        offsets, off = [], 0
+        for n in sizes:
+            targets.append({"gt_boxes": boxes[off:off + n], "labels": labels[off:off + n]})
+            offsets.append(off)
+            off += n
+        targets.labels_cat, targets.boxes_cat, targets.offsets = labels, boxes, offsets
         return targets
 
     def extract(self, batched_inputs):
@@ -158,17 +180,30 @@ class VoxelDETR(nn.Module):
         return self.postprocess(cls_out[-1], box_out[-1])
 
     def losses(self, cls_out, box_out, memory, anchors, topk_idx, targets):
+        """Encoder-proposal and decoder losses.  The cost matrices of all four matchings (encoder + 3
+        decoder layers) are built on the GPU and solved after ONE device-to-host transfer; the assignments
+        go back in one pinned non-blocking copy (the reference syncs once per layer and per index tensor,
+        VD/modules/matcher.py:86, VD/losses.py:17-48)."""
+        from .losses import TargetList, upload_matches
+
         losses = {}
-        prop = self.transformer.proposal_head
+        prop, head = self.transformer.proposal_head, self.transformer.decoder.detection_head
         num_boxes = prop.losses.normaliser(targets, cls_out.device)
         enc_cls, enc_box = prop(memory, anchors)
-        bin_targets = [dict(t, labels=torch.zeros_like(t["labels"])) for t in targets]
-        enc = prop.compute_losses({"topk_indexes": topk_idx, "pred_logits": enc_cls, "pred_boxes": enc_box},
-                                  bin_targets, num_boxes)
-        losses.update({k + "_enc": v for k, v in enc.items()})
-        outputs = {"pred_logits": cls_out[-1], "pred_boxes": box_out[-1],
+        bin_targets = TargetList(dict(t, labels=torch.zeros_like(t["labels"])) for t in targets)
+        bin_targets.labels_cat = torch.zeros_like(targets.labels_cat)
+        bin_targets.boxes_cat, bin_targets.offsets = targets.boxes_cat, targets.offsets
+        enc_out = {"topk_indexes": topk_idx, "pred_logits": enc_cls, "pred_boxes": enc_box}
+        dec_out = {"pred_logits": cls_out[-1], "pred_boxes": box_out[-1],
                    "aux_outputs": [{"pred_logits": a, "pred_boxes": b} for a, b in zip(cls_out[:-1], box_out[:-1])]}
-        losses.update(self.transformer.decoder.detection_head.compute_losses(outputs, targets, num_boxes))
+        mats = prop.losses.prepare(enc_out, bin_targets) + head.losses.prepare(dec_out, targets)
+        solved = head.losses.matcher.solve(mats)  # the one host round trip of the loss
+        bs = len(targets)
+        per_layer = [solved[i * bs:(i + 1) * bs] for i in range(len(solved) // max(bs, 1))]
+        matches = upload_matches(per_layer, targets.offsets, cls_out.device)
+        enc = prop.compute_losses(enc_out, bin_targets, num_boxes, solved=matches[:1])
+        losses.update({k + "_enc": v for k, v in enc.items()})
+        losses.update(head.compute_losses(dec_out, targets, num_boxes, solved=matches[1:]))
         return losses
 
     def postprocess(self, logits, boxes):

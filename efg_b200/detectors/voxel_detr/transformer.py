@@ -167,10 +167,14 @@ class Transformer(nn.Module):
     def encode(self, src, pos):
         assert pos is not None, "position encoding is required!"
         anchors = self._create_ref_windows(src)
-        shapes = torch.tensor([[t.shape[2], t.shape[3]] for t in src], dtype=torch.int64, device=src[0].device)
+        key = ("shapes", tuple((t.shape[2], t.shape[3]) for t in src), src[0].device)
+        if key not in self._ref_cache:  # level shapes / start offsets are constants of the BEV geometry
+            shapes = torch.tensor([[t.shape[2], t.shape[3]] for t in src], dtype=torch.int64, device=src[0].device)
+            start = torch.cat([shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]])
+            self._ref_cache[key] = (shapes, start)
+        shapes, start = self._ref_cache[key]
         flat = torch.cat([t.flatten(2).transpose(1, 2) for t in src], dim=1)
         flat_pos = torch.cat([p.flatten(2).transpose(1, 2) for p in pos], dim=1)
-        start = torch.cat([shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]])
         memory = self.encoder(flat, flat_pos, shapes, start, anchors)
         return memory, anchors, shapes, start
 

@@ -129,6 +129,7 @@ class SparseResNet(nn.Module):
         x = sp.SparseConvTensor(voxel_features, coors.int(), sparse_shape, batch_size)
         wanted = self._out_features if self.compute_features is None else \
             [f for f in self._out_features if f in self.compute_features]
+        self._plan_rulebooks(x, wanted)
         stage_out = {}
         x = self.stem(x)
         if "stem" in wanted:
@@ -143,6 +144,28 @@ class SparseResNet(nn.Module):
             n, c, d, h, w = out.shape
             outputs[f] = out.view(n, c * d, h, w)
         return outputs
+
+    def _plan_rulebooks(self, x, wanted):
+        """Build every strided rulebook of the forward pass up front (indices only).  Each one needs a host
+        read of its output count; doing them back to back, before any feature kernel is queued, keeps
+        those synchronisations from draining the GPU in the middle of the feature pipeline."""
+        sp = self._sp[0]
+        plan = getattr(sp, "strided_rulebook", None)
+        if plan is None:
+            return
+        cur = x
+        levels = {}
+        rb = plan(cur, 3, 2, 1)  # stem conv
+        cur = sp.SparseConvTensor(None, rb.out_indices, rb.out_shape, x.batch_size, indice_dict=x.indice_dict)
+        cur._rows_sorted = True
+        for _, name in self.stages_and_names:
+            rb = plan(cur, 3, 2, 1)  # first block of the stage: main + shortcut conv share it
+            cur = sp.SparseConvTensor(None, rb.out_indices, rb.out_shape, x.batch_size, indice_dict=x.indice_dict)
+            cur._rows_sorted = True
+            levels[name] = cur
+        for f in wanted:
+            if f in levels:
+                plan(levels[f], (3, 1, 1), (2, 1, 1), (1, 0, 0))
 
     def output_shape(self):
         return {n: {"channels": self._out_feature_channels[n], "stride": self._out_feature_strides[n]}

@@ -141,6 +141,21 @@ class _SparseConvFn(Function):
         return d_feat, d_w, d_b, None
 
 
+def strided_rulebook(x, kernel_size, stride, padding):
+    """Rulebook of a regular sparse conv over ``x``'s active set, cached on the tensor by geometry: the
+    main and the shortcut conv of a residual block (sparse_net.py:126,136) share one table (and one host
+    sync), and a backbone can build all of them ahead of the feature pass (SparseResNet.forward)."""
+    k, s_, p_ = _triple(kernel_size), _triple(stride), _triple(padding)
+    key = ("__strided__", id(x.indices), tuple(k), tuple(s_), tuple(p_))
+    cached = x.indice_dict.get(key)
+    if cached is not None and cached.in_indices is x.indices:
+        return cached
+    out_indices, out_shape, nbr, nbr_t = ops.sparse_rulebook(x.indices, x.batch_size, x.spatial_shape, k, s_, p_)
+    rb = _Rulebook(nbr, nbr_t, False, out_indices, out_shape, k, x.indices)
+    x.indice_dict[key] = rb
+    return rb
+
+
 class SparseModule(nn.Module):
     """Marker base class: SparseSequential hands these the SparseConvTensor itself."""
 
@@ -249,9 +264,7 @@ class SparseConvolution(SparseModule):
                                     rows_sorted=x._rows_sorted)
             rb = _Rulebook(nbr, None, True, x.indices, x.spatial_shape, self.kernel_size, x.indices)
         else:
-            out_indices, out_shape, nbr, nbr_t = ops.sparse_rulebook(x.indices, x.batch_size, x.spatial_shape,
-                                                                    self.kernel_size, self.stride, self.padding)
-            rb = _Rulebook(nbr, nbr_t, False, out_indices, out_shape, self.kernel_size, x.indices)
+            rb = strided_rulebook(x, self.kernel_size, self.stride, self.padding)
         if self.indice_key is not None:
             x.indice_dict[self.indice_key] = rb
         return rb
