@@ -117,3 +117,45 @@ def voxel_detr_config(**overrides):
     if overrides:
         cfg = merge(cfg, overrides)
     return to_config(cfg)
+
+
+def conquer_config(**overrides):
+    """ConQueR = Voxel-DETR + contrastive / denoising keys (CQ/config.yaml:133-144)."""
+    extra = {"model": {"contrastive": {"mom": 0.999, "dim": 256, "eqco": 1000, "tau": 0.7, "loss_coeff": 0.2},
+                       "dn": {"enabled": True, "dn_number": 3, "dn_box_noise_scale": 0.4, "dn_label_noise_ratio": 0.5}}}
+    cfg = merge(voxel_detr_config(), extra)
+    if overrides:
+        cfg = merge(cfg, overrides)
+    return to_config(cfg)
+
+
+# playground/detection.3d/waymo/center_point/centerpoint.waymo.voxelnet...bs48.36e/config.yaml:60-115
+CENTERPOINT_WAYMO = {
+    "dataset": {"classes": ["VEHICLE", "PEDESTRIAN", "CYCLIST"], "pc_range": [-75.2, -75.2, -2.0, 75.2, 75.2, 4.0],
+                "voxel_size": [0.1, 0.1, 0.15], "max_points_in_voxel": 5, "max_voxel_num": 150000},
+    "model": {
+        "device": "cuda",
+        "reader": {"num_input_features": 5, "norm": "BN"},
+        "backbone": {"num_input_features": 5, "norm": "BN1d"},
+        "neck": {"num_input_features": 256, "layer_nums": [5, 5], "ds_layer_strides": [1, 2], "ds_num_filters": [128, 256],
+                 "us_layer_strides": [1, 2], "us_num_filters": [256, 256], "norm": "BN"},
+        "head": {"in_channels": 512, "norm": {"type": "BN"},
+                 "tasks": [{"num_classes": 3, "class_names": ["VEHICLE", "PEDESTRIAN", "CYCLIST"]}],
+                 "misc": {"dataset": "waymo", "weight": 2, "code_weights": [1.0] * 8,
+                          "common_heads": {"reg": [2, 2], "height": [1, 2], "dim": [3, 2], "rot": [2, 2]}}},
+        "loss": {"out_size_factor": 8, "dense_reg": 1, "gaussian_overlap": 0.1, "max_objs": 500, "min_radius": 2},
+        "post_process": {"post_center_limit_range": [-80, -80, -10.0, 80, 80, 10.0],
+                         "nms": {"nms_pre_max_size": 4096, "nms_post_max_size": 300, "nms_iou_threshold": 0.7},
+                         "score_threshold": 0.1, "pc_range": [-75.2, -75.2, -2.0, 75.2, 75.2, 4.0], "out_size_factor": 8,
+                         "voxel_size": [0.1, 0.1, 0.15]},
+    },
+}
+
+
+def centerpoint_config(**overrides):
+    cfg = copy.deepcopy(CENTERPOINT_WAYMO)
+    if overrides:
+        cfg = merge(cfg, overrides)
+    cfg["model"]["post_process"]["pc_range"] = cfg["dataset"]["pc_range"]
+    cfg["model"]["post_process"]["voxel_size"] = cfg["dataset"]["voxel_size"]
+    return to_config(cfg)

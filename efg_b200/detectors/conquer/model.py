@@ -1,0 +1,225 @@
+"""ConQueR (CQ/voxel_detr.py, CQ/transformer.py, CQ/losses.py, CQ/cdn.py): Voxel-DETR plus
+  * contrastive denoising queries prepended to the decoder input (cdn.py),
+  * a momentum (EMA, m = 0.999) copy of the decoder that decodes the clean and the positively-noised
+    ground-truth boxes without gradient (CQ/transformer.py:84-89, 134-177),
+  * denoising losses on the noised positives (CQ/losses.py:154-207),
+  * a query-contrast InfoNCE loss between projected GT-decoder outputs and the predictor of the matched
+    queries, tau = 0.7 (CQ/voxel_detr.py:222-254) — vectorised here, same value.
+"""
+import copy
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from ..voxel_detr.losses import MatchIndex, TargetList, upload_matches
+from ..voxel_detr.model import VoxelDETR
+from ..voxel_detr.transformer import Transformer
+from .cdn import dn_post_process, prepare_for_cdn
+
+
+class ConQueRTransformer(Transformer):
+    def __init__(self, *args, num_classes=3, mom=0.999, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.num_classes = num_classes
+        self.m = mom
+        self.decoder_gt = None  # EMA copy, attached by the detector after the heads exist
+
+    @torch.no_grad()
+    def _momentum_update_gt_decoder(self):
+        q = [p.data for p in self.decoder.parameters()]
+        k = [p.data for p in self.decoder_gt.parameters()]
+        torch._foreach_mul_(k, self.m)
+        torch._foreach_add_(k, q, alpha=1.0 - self.m)
+
+    def forward(self, src, pos, noised_gt_box=None, noised_gt_onehot=None, attn_mask=None, targets=None):
+        memory, anchors, shapes, start = self.encode(src, pos)
+        query_embed, query_pos, proposals, topk_indexes = self._get_enc_proposals(memory, anchors)
+        noised = None
+        if noised_gt_box is not None:
+            noised = torch.cat((noised_gt_box, noised_gt_onehot), dim=-1)
+            proposals = torch.cat((noised, proposals), dim=1)
+        init_ref = proposals[..., :7]
+        hs, inter_refs = self.decoder(query_embed, query_pos, memory, shapes, start, proposals, attn_mask)
+
+        if targets is not None:  # momentum GT decoder: clean GT + positively noised GT groups, no gradient
+            per_gt = [int(t["gt_boxes"].shape[0]) for t in targets]
+            max_gt = max(per_gt)
+            gt = memory.new_zeros(len(targets), max_gt, 10)
+            for bi, t in enumerate(targets):
+                gt[bi, :per_gt[bi], :7] = t["gt_boxes"]
+                gt[bi, :per_gt[bi], 7:] = F.one_hot(t["labels"], num_classes=self.num_classes).to(gt.dtype)
+            with torch.no_grad():
+                self._momentum_update_gt_decoder()
+                if noised is not None:
+                    groups = noised.shape[1] // (max_gt * 2)
+                    pos_noised = torch.cat([noised[:, pi * max_gt:(pi + 1) * max_gt] for pi in range(0, groups * 2, 2)], dim=1)
+                    gt_proposals = torch.cat((gt, pos_noised), dim=1)
+                    n = (groups + 1) * max_gt
+                    gt_mask = torch.ones(n, n, dtype=torch.bool, device=memory.device)
+                    for di in range(groups + 1):
+                        gt_mask[di * max_gt:(di + 1) * max_gt, di * max_gt:(di + 1) * max_gt] = False
+                else:
+                    gt_proposals, gt_mask = gt, None
+                hs_gt, refs_gt = self.decoder_gt(None, None, memory, shapes, start, gt_proposals, gt_mask)
+            init_ref = torch.cat((init_ref, gt_proposals[..., :7]), dim=1)
+            hs = torch.cat((hs, hs_gt), dim=2)
+            inter_refs = torch.cat((inter_refs, refs_gt), dim=2)
+        return hs, init_ref, inter_refs, memory, anchors, topk_indexes
+
+
+class ConQueR(VoxelDETR):
+    def __init__(self, config, backend=None, prune_unused=True):
+        super().__init__(config, backend=backend, prune_unused=prune_unused)
+        tr = self.transformer
+        tr.decoder_gt = copy.deepcopy(tr.decoder)  # includes its own copy of the detection head
+        for p in tr.decoder_gt.parameters():
+            p.requires_grad = False
+        c = config.model.contrastive
+        self.tau = c.tau
+        self.contras_loss_coeff = c.loss_coeff
+        self.projector = nn.Sequential(nn.Linear(10, c.dim), nn.ReLU(), nn.Linear(c.dim, c.dim))
+        self.predictor = nn.Sequential(nn.Linear(c.dim, c.dim), nn.ReLU(), nn.Linear(c.dim, c.dim))
+        self.cdn_noise = None  # optional externally supplied noise (parity tests)
+        self.to(self.device)
+
+    def _build_transformer(self, config, t):
+        return ConQueRTransformer(d_model=t.hidden_dim, nhead=t.nhead, nlevel=len(config.model.backbone.out_features),
+                                  num_encoder_layers=t.enc_layers, num_decoder_layers=t.dec_layers,
+                                  dim_feedforward=t.dim_feedforward, dropout=t.dropout, num_queries=t.num_queries,
+                                  backend=self.backend[0], num_classes=len(config.dataset.classes),
+                                  mom=config.model.contrastive.mom)
+
+    def forward(self, batched_inputs):
+        targets = self.encode_targets(batched_inputs) if self.training else None
+        features, pos = self.extract(batched_inputs)
+        dn = self.config.model.dn
+        if self.training and dn.enabled and dn.dn_number > 0:
+            q_label, q_box, attn_mask, dn_meta = prepare_for_cdn(targets, dn.dn_number, dn.dn_label_noise_ratio,
+                                                                 dn.dn_box_noise_scale, self.num_queries,
+                                                                 self.num_classes, noise=self.cdn_noise)
+        else:
+            q_label = q_box = attn_mask = dn_meta = None
+        hs, init_ref, inter_refs, memory, anchors, topk_idx = self.transformer(features, pos, q_box, q_label, attn_mask,
+                                                                              targets=targets)
+        head = self.transformer.decoder.detection_head
+        cls_out, box_out = [], []
+        for i in range(hs.shape[0]):
+            ref = init_ref if i == 0 else inter_refs[i - 1]
+            c, b = head(hs[i], ref, i)
+            cls_out.append(c)
+            box_out.append(b)
+        cls_out, box_out = torch.stack(cls_out), torch.stack(box_out)
+        if dn_meta is not None:
+            cls_out, box_out = dn_post_process(cls_out, box_out, dn_meta, self.aux_loss)
+        if not self.training:
+            return self.postprocess_threshold(cls_out[-1][:, :self.num_queries], box_out[-1][:, :self.num_queries])
+        return self.conquer_losses(cls_out, box_out, memory, anchors, topk_idx, targets, dn_meta)
+
+    # ---------------------------------------------------------------------------------------
+    def conquer_losses(self, cls_out, box_out, memory, anchors, topk_idx, targets, dn_meta):
+        nq = self.num_queries
+        prop, head = self.transformer.proposal_head, self.transformer.decoder.detection_head
+        num_boxes = prop.losses.normaliser(targets, cls_out.device)
+        enc_cls, enc_box = prop(memory, anchors)
+        bin_targets = TargetList(dict(t, labels=torch.zeros_like(t["labels"])) for t in targets)
+        bin_targets.labels_cat = torch.zeros_like(targets.labels_cat)
+        bin_targets.boxes_cat, bin_targets.offsets = targets.boxes_cat, targets.offsets
+        enc_out = {"topk_indexes": topk_idx, "pred_logits": enc_cls, "pred_boxes": enc_box}
+        dec_out = {"pred_logits": cls_out[-1][:, :nq], "pred_boxes": box_out[-1][:, :nq],
+                   "aux_outputs": [{"pred_logits": a[:, :nq], "pred_boxes": b[:, :nq]}
+                                   for a, b in zip(cls_out[:-1], box_out[:-1])]}
+        mats = prop.losses.prepare(enc_out, bin_targets) + head.losses.prepare(dec_out, targets)
+        solved = head.losses.matcher.solve(mats)
+        bs = len(targets)
+        per_layer = [solved[i * bs:(i + 1) * bs] for i in range(len(solved) // max(bs, 1))]
+        matches = upload_matches(per_layer, targets.offsets, cls_out.device)
+        losses = {k + "_enc": v for k, v in prop.compute_losses(enc_out, bin_targets, num_boxes, solved=matches[:1]).items()}
+        losses.update(head.compute_losses(dec_out, targets, num_boxes, solved=matches[1:]))
+        if dn_meta is not None:
+            losses.update(self.dn_losses(head, dn_meta, targets, num_boxes))
+        losses.update(self.contrastive_losses(cls_out, box_out, matches[-1], targets, dn_meta))
+        return losses
+
+    def dn_losses(self, head, dn_meta, targets, num_boxes):
+        """Losses of the positively noised queries against their own GT (CQ/losses.py:154-207).  The reference
+        builds the target index as ``arange(0, len(labels) - 1)`` — the LAST ground-truth box of every scene is
+        left out; kept as is for identical results."""
+        known = dn_meta["output_known_lbs_bboxes"]
+        groups, pad = dn_meta["num_dn_group"], dn_meta["pad_size"]
+        assert pad % groups == 0
+        single_pad = pad // groups
+        dev = targets.boxes_cat.device
+        b_l, s_l, t_l = [], [], []
+        for i, t in enumerate(targets):
+            n = int(t["labels"].shape[0])
+            if n > 0:
+                tt = torch.arange(0, n - 1).repeat(groups)
+                out_idx = (torch.arange(groups) * single_pad).repeat_interleave(max(n - 1, 0)) + tt
+                b_l.append(torch.full_like(tt, i))
+                s_l.append(out_idx)
+                t_l.append(tt + targets.offsets[i])
+        if b_l:
+            idx = torch.stack([torch.cat(b_l), torch.cat(s_l), torch.cat(t_l)])
+        else:
+            idx = torch.zeros((3, 0), dtype=torch.int64)
+        if dev.type == "cuda":
+            idx = idx.pin_memory().to(dev, non_blocking=True)
+        match = MatchIndex(idx[0], idx[1], idx[2])
+        weights = head.losses.weight_dict
+        out = {}
+        layers = list(known.get("aux_outputs", [])) + [{k: v for k, v in known.items() if k != "aux_outputs"}]
+        for li, lo in enumerate(layers):
+            suffix = "_dn" if li == len(layers) - 1 else "_dn_{}".format(li)
+            for loss in head.losses.losses:
+                for k, v in head.losses.det3d_losses[loss](lo, targets, match, num_boxes * groups).items():
+                    out[k + suffix] = v * weights.get(k, 1.0)
+        return out
+
+    def contrastive_losses(self, cls_out, box_out, final_match, targets, dn_meta):
+        """InfoNCE between the (detached) GT-decoder outputs of the noised-GT groups and the predictor of the
+        matched queries; negatives are the unmatched queries (CQ/voxel_detr.py:222-254, vectorised)."""
+        out = {}
+        per_gt = [int(t["gt_boxes"].shape[0]) for t in targets]
+        num_gts, max_gt = sum(per_gt), max(per_gt)
+        if num_gts == 0 or dn_meta is None:
+            return out
+        nq, groups = self.num_queries, dn_meta["num_dn_group"]
+        B = cls_out.shape[1]
+        dev = cls_out.device
+        b_idx, q_idx = final_match.batch, final_match.src
+        offs = torch.tensor(targets.offsets, dtype=torch.int64)
+        if dev.type == "cuda":
+            offs = offs.pin_memory().to(dev, non_blocking=True)
+        local_t = final_match.tgt - offs[b_idx]                                   # GT index inside its scene
+        neg_mask = torch.ones(B, nq, dtype=torch.bool, device=dev)
+        neg_mask[b_idx, q_idx] = False
+        pos_rows = local_t[:, None] + max_gt * torch.arange(1, groups + 1, device=dev)[None, :]  # [P, groups]
+        for li in range(cls_out.shape[0]):
+            projs = torch.cat((cls_out[li], box_out[li]), dim=-1)
+            gt_projs = F.normalize(self.projector(projs[:, nq:].detach()), dim=-1, eps=1e-8)
+            pred_projs = F.normalize(self.predictor(self.projector(projs[:, :nq])), dim=-1, eps=1e-8)
+            sim = torch.einsum("bgc,bqc->bgq", gt_projs, pred_projs) / self.tau      # [B, G, nq]
+            rows = sim[b_idx[:, None], pos_rows]                                     # [P, groups, nq]
+            pos = torch.gather(rows, 2, q_idx[:, None, None].expand(-1, groups, 1))  # [P, groups, 1]
+            neg = (torch.exp(rows) * neg_mask[b_idx][:, None, :]).sum(-1, keepdim=True)
+            loss = torch.log(torch.exp(pos) + neg) - pos
+            out["loss_contrastive_dec_{}".format(li)] = self.contras_loss_coeff * loss.mean(dim=1).sum() / num_gts
+        return out
+
+    def postprocess_threshold(self, logits, boxes):
+        """Evaluation output of ConQueR: every (query, class) with score >= 0.1 (CQ/voxel_detr.py:258-285;
+        like the reference this assumes one scene per batch for the flattened index)."""
+        prob = logits.sigmoid().view(logits.shape[0], -1)
+        boxes = self.box_coder.decode(boxes)
+        results = []
+        for b in range(prob.shape[0]):
+            keep = torch.nonzero(prob[b] >= 0.1, as_tuple=True)[0]
+            q = keep.div(logits.shape[2], rounding_mode="floor")
+            results.append({"scores": prob[b, keep].detach().cpu(), "labels": (keep % logits.shape[2] + 1).detach().cpu(),
+                            "boxes3d": boxes[b, q].detach().cpu()})
+        return results
+
+
+def build_model(self, config, backend=None):
+    return ConQueR(config, backend=backend)

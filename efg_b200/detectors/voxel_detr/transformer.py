@@ -154,11 +154,13 @@ class Transformer(nn.Module):
     def _get_enc_proposals(self, enc_embed, ref_windows):
         logits, windows = self.proposal_head(enc_embed, ref_windows)
         probs = logits[..., 0].sigmoid()
-        topk_probs, indexes = torch.topk(probs, self.num_queries, dim=1, sorted=False)
-        # the reference leaves the proposal order to topk(sorted=False); canonicalise it (ascending
-        # BEV index) so runs on different devices enumerate the same query set identically
-        indexes, order = indexes.sort(dim=1)
-        topk_probs = torch.gather(topk_probs, 1, order)
+        # The reference takes topk(sorted=False): which of several EQUAL scores survive, and in which order,
+        # is unspecified (empty BEV cells produce bit-identical scores).  Canonical choice here: a stable
+        # descending sort (ties -> lowest BEV index), then ascending index order, so every device
+        # enumerates the same query set identically.
+        order = torch.argsort(probs, dim=1, descending=True, stable=True)[:, :self.num_queries]
+        indexes, _ = order.sort(dim=1)
+        topk_probs = torch.gather(probs, 1, indexes)
         indexes = indexes.unsqueeze(-1)
         windows = torch.gather(windows, 1, indexes.expand(-1, -1, windows.shape[-1]))
         windows = torch.cat((windows.detach(), topk_probs.detach().unsqueeze(-1).expand(-1, -1, 3)), dim=-1)

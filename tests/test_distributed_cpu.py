@@ -1,0 +1,73 @@
+"""CPU, world_size 2 over gloo: the data-parallel plumbing (parameter broadcast, bucketed gradient
+averaging, the num_boxes all-reduce of the loss) reproduces single-process gradients."""
+import os
+import socket
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from efg_b200.detectors.voxel_detr.losses import Det3DLoss
+    from efg_b200.parallel import GradAverager, init_distributed
+
+    r, _, w = init_distributed("gloo")
+    assert (r, w) == (rank, world)
+    torch.manual_seed(100 + rank)  # different initial weights per rank: broadcast must fix that
+    model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+    unused = torch.nn.Linear(3, 3)  # never used: has no gradient on any rank (like the pruned FPN levels)
+    holder = torch.nn.ModuleList([model, unused])
+    avg = GradAverager(holder, bucket_bytes=256)  # tiny buckets -> several all-reduces
+    avg.broadcast_parameters()
+    torch.manual_seed(7)
+    data = torch.randn(2, 6, 8)
+    loss = model(data[rank]).square().mean()
+    loss.backward()
+    nbytes = avg.average_gradients()
+    assert nbytes == sum(p.numel() * 4 for p in model.parameters())
+    assert all(p.grad is None for p in unused.parameters())
+    # loss normaliser: mean number of boxes per rank, all-reduced (VD/losses.py:121-125)
+    targets = [{"labels": torch.zeros(3 + 4 * rank, dtype=torch.long)}]
+    nb = Det3DLoss.normaliser(targets, torch.device("cpu"))
+    torch.save({"grads": [p.grad.clone() for p in model.parameters()], "params": [p.detach().clone() for p in model.parameters()],
+                "num_boxes": nb}, os.path.join(out_dir, "rank%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_average_matches_single_process(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0 = torch.load(tmp_path / "rank0.pt")
+    r1 = torch.load(tmp_path / "rank1.pt")
+    for a, b in zip(r0["params"], r1["params"]):
+        assert torch.equal(a, b)  # broadcast from rank 0
+    for a, b in zip(r0["grads"], r1["grads"]):
+        assert torch.equal(a, b)  # both ranks hold the averaged gradient
+    assert r0["num_boxes"] == r1["num_boxes"] == (3 + 7) / 2
+    # single-process reference: mean of the two per-rank losses
+    torch.manual_seed(100)
+    model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+    with torch.no_grad():
+        for p, q in zip(model.parameters(), r0["params"]):
+            p.copy_(q)
+    torch.manual_seed(7)
+    data = torch.randn(2, 6, 8)
+    (0.5 * (model(data[0]).square().mean() + model(data[1]).square().mean())).backward()
+    for p, g in zip(model.parameters(), r0["grads"]):
+        assert torch.allclose(p.grad, g, atol=1e-6)
