@@ -115,12 +115,15 @@ struct Params {
   const float* in;       // [num_in, c_red]
   const float* packed;   // [chunks][parts][n_out][32] swizzled image
   const float* bias;     // [n_out] or null
-  const int32_t* nbr;    // [num_out, taps]
+  const int32_t* nbr;    // [num_out, taps], or null = identity (dense GEMM: taps == 1, src row = out row)
   float* out;            // [num_out, n_out]
   int64_t num_out;
   int c_red, taps, n_out, chunks;
-  int num_tiles;
+  int num_tiles;         // 128-row tiles
   int n_cta;             // output columns per CTA (n_out / gridDim.y)
+  int tiles_per_super;   // T: row tiles that share every weight chunk (accumulators side by side in TMEM)
+  int num_super;         // ceil(num_tiles / T)
+  int sa, sb;            // A-ring / B-ring depth
   int debug;             // perf experiments only: 1 = no MMAs, 2 = no gather loads, 4 = no index loads
 };
 
@@ -129,61 +132,105 @@ struct Smem {
   static constexpr int kParts = kSplit ? 2 : 1;
   static __host__ __device__ int a_bytes() { return kParts * kTileM * 128; }
   static __host__ __device__ int b_bytes(int n) { return kParts * n * 128; }
-  static __host__ __device__ int stage_bytes(int n) { return a_bytes() + b_bytes(n); }
 };
 
-__host__ inline int pick_stages(int stage_bytes, int nbr_bytes) {
-  const int budget = 227 * 1024 - 2048 - nbr_bytes;
-  int s = budget / stage_bytes;
-  if (s > 6) s = 6;
-  return s;
-}
+// Work of one CTA: super-tiles st = blockIdx.x + i * gridDim.x; a super-tile is T consecutive 128-row tiles
+// (the globally last one may hold fewer).  The A-stage stream of the CTA is ordered (super-tile, chunk, tile).
+struct CtaWork {
+  int n_super;      // super-tiles of this CTA
+  int t_last;       // tiles in this CTA's last super-tile
+  int total_a;      // A stages of this CTA
+  __device__ __forceinline__ CtaWork(const Params& p) {
+    n_super = (p.num_super - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    if (n_super < 0) n_super = 0;
+    t_last = p.tiles_per_super;
+    if (n_super > 0) {
+      const int st_last = static_cast<int>(blockIdx.x) + (n_super - 1) * static_cast<int>(gridDim.x);
+      const int rem = p.num_tiles - st_last * p.tiles_per_super;
+      if (rem < t_last) t_last = rem;
+    }
+    total_a = n_super > 0 ? ((n_super - 1) * p.tiles_per_super + t_last) * p.chunks : 0;
+  }
+  __device__ __forceinline__ int tiles_in(const Params& p, int i) const { return i == n_super - 1 ? t_last : p.tiles_per_super; }
+  // A-stage index -> (tile, chunk)
+  __device__ __forceinline__ void locate(const Params& p, int ga, int* tile, int* chunk) const {
+    const int full = (n_super - 1) * p.chunks * p.tiles_per_super;
+    int i, c, t;
+    if (ga < full) {
+      const int per = p.chunks * p.tiles_per_super;
+      i = ga / per;
+      const int rem = ga - i * per;
+      c = rem / p.tiles_per_super;
+      t = rem - c * p.tiles_per_super;
+    } else {
+      const int rem = ga - full;
+      i = n_super - 1;
+      c = rem / t_last;
+      t = rem - c * t_last;
+    }
+    *tile = (static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x)) * p.tiles_per_super + t;
+    *chunk = c;
+  }
+};
 
-// A producers.  kGroups warp groups; group g owns every kGroups-th K chunk of this CTA's chunk stream, so
-// kGroups chunks are gathered concurrently and every thread keeps 1024/(threads per group) independent
-// 16-byte loads in flight (the gather is latency-bound otherwise).  The rulebook entry is read straight
-// from global memory (8 lanes share one entry -> broadcast); the smem slot is only waited for AFTER the
-// loads were issued.  kGroups must not exceed the number of stages: a group that is a full ring ahead of
-// the MMA would otherwise see an aliased mbarrier parity.
+// A producers.  kGroups warp groups; group g owns every kGroups-th A stage of this CTA's stream, so kGroups
+// stages are gathered concurrently and every thread keeps 1024/(threads per group) independent 16-byte loads
+// in flight.  The rulebook entries of a group's NEXT stage are fetched while the gathers of the current one
+// are in flight, and the smem slot is only waited for after the loads were issued, so a stage costs one memory
+// latency.  kGroups must not exceed the A-ring depth (mbarrier parity would alias).
 template <bool kSplit, int kGroups>
-__device__ __forceinline__ void produce_a(const Params& p, const int stages, uint8_t* stage_base, const int stage_bytes,
-                                          uint64_t* full_bar, uint64_t* empty_bar, const int warp, const int lane) {
+__device__ __forceinline__ void produce_a(const Params& p, const CtaWork& w, uint8_t* a_ring, uint64_t* a_full,
+                                          uint64_t* a_empty, const int warp, const int lane) {
   constexpr int kWarpsPerGroup = kProducerWarps / kGroups;
-  constexpr int kPieces = (kTileM * 8) / (kWarpsPerGroup * 32);  // 16-byte pieces per thread per chunk
+  constexpr int kPieces = (kTileM * 8) / (kWarpsPerGroup * 32);  // 16-byte pieces per thread per stage
   const int a_part = kTileM * 128;
+  const int a_bytes = Smem<kSplit>::a_bytes();
   const int gidx = warp / kWarpsPerGroup;
   const int gw = warp % kWarpsPerGroup;
   const int row_in_group = lane >> 3;  // 0..3
   const int q = lane & 7;              // 16-byte piece of the 128-byte row
-  const int my_tiles = (p.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-  const int64_t total_chunks = static_cast<int64_t>(my_tiles) * p.chunks;
-  for (int64_t gc = gidx; gc < total_chunks; gc += kGroups) {
-    const int ti = static_cast<int>(gc / p.chunks);
-    const int c = static_cast<int>(gc - static_cast<int64_t>(ti) * p.chunks);
-    const int stage = static_cast<int>(gc % stages);
-    const uint32_t phase = static_cast<uint32_t>((gc / stages) & 1);
-    const int64_t r0 = (static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(ti) * gridDim.x) * kTileM;
-    const int kk = c * kChunkK + q * 4;  // first K index of this lane's 16-byte piece
+
+  int32_t src_next[kPieces];
+  int tile_n = 0, chunk_n = 0;
+  auto load_indices = [&](int ga) {
+    w.locate(p, ga, &tile_n, &chunk_n);
+    const int64_t r0 = static_cast<int64_t>(tile_n) * kTileM;
+    const int kk = chunk_n * kChunkK + q * 4;
     const int tap = kk / p.c_red;
-    const int ci = kk - tap * p.c_red;
     const bool tap_ok = tap < p.taps;
-    int32_t src[kPieces];
 #pragma unroll
     for (int i = 0; i < kPieces; ++i) {
       const int64_t row = r0 + (i * kWarpsPerGroup + gw) * 4 + row_in_group;
-      src[i] = (tap_ok && row < p.num_out && !(p.debug & 4)) ? __ldg(p.nbr + row * p.taps + tap) : -1;
+      int32_t v = -1;
+      if (tap_ok && row < p.num_out && !(p.debug & 4)) v = p.nbr ? __ldg(p.nbr + row * p.taps + tap) : static_cast<int32_t>(row);
+      src_next[i] = v;
     }
+  };
+
+  int ga = gidx;
+  if (ga < w.total_a) load_indices(ga);
+  while (ga < w.total_a) {
+    const int kk = chunk_n * kChunkK + q * 4;
+    const int tap = kk / p.c_red;
+    const int ci = kk - tap * p.c_red;
     float4 v[kPieces];
 #pragma unroll
     for (int i = 0; i < kPieces; ++i) {
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (src[i] >= 0 && !(p.debug & 2)) v[i] = __ldg(reinterpret_cast<const float4*>(p.in + static_cast<int64_t>(src[i]) * p.c_red + ci));
+      if (src_next[i] >= 0 && !(p.debug & 2))
+        v[i] = __ldg(reinterpret_cast<const float4*>(p.in + static_cast<int64_t>(src_next[i]) * p.c_red + ci));
     }
-    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-    uint8_t* a_hi = stage_base + static_cast<size_t>(stage) * stage_bytes;
+    const int round = ga / p.sa;
+    const int stage = ga - round * p.sa;
+    const uint32_t phase = static_cast<uint32_t>(round & 1);
+    const int ga_next = ga + kGroups;
+    if (ga_next < w.total_a) load_indices(ga_next);  // overlaps with the gathers above
+    mbar_wait(smem_u32(&a_empty[stage]), phase ^ 1);
+    uint8_t* a_hi = a_ring + static_cast<size_t>(stage) * a_bytes;
     uint8_t* a_lo = a_hi + a_part;
 #pragma unroll
     for (int i = 0; i < kPieces; ++i) {
+      if (p.debug & 8) break;
       const int r = (i * kWarpsPerGroup + gw) * 4 + row_in_group;
       const uint32_t off = static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(q ^ (r & 7)) << 4);
       if (kSplit) {
@@ -202,43 +249,53 @@ __device__ __forceinline__ void produce_a(const Params& p, const int stages, uin
         *reinterpret_cast<float4*>(a_hi + off) = v[i];
       }
     }
-    fence_proxy_async();  // make the generic-proxy stores visible to the tensor core (async proxy)
+    if (!(p.debug & 16)) fence_proxy_async();  // make the generic-proxy stores visible to the tensor core (async proxy)
     __syncwarp();
-    if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
+    if (lane == 0) mbar_arrive(smem_u32(&a_full[stage]));
+    ga = ga_next;
   }
 }
 
 template <bool kSplit>
-__global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p, const int stages) {
+__global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the swizzle atoms
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int n_cta = p.n_cta;                       // output columns owned by this CTA (N split over grid.y)
+  constexpr int kParts = Smem<kSplit>::kParts;
+  const int n_cta = p.n_cta;  // output columns owned by this CTA (N split over grid.y)
   const int n0 = static_cast<int>(blockIdx.y) * n_cta;
-  const int stage_bytes = Smem<kSplit>::stage_bytes(n_cta);
+  const int T = p.tiles_per_super;
+  const int a_bytes = Smem<kSplit>::a_bytes();
+  const int b_bytes = Smem<kSplit>::b_bytes(n_cta);
   const int a_part = kTileM * 128;
   const int b_part = n_cta * 128;
-  uint8_t* stage_base = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * stage_bytes);
-  // bars: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then the TMEM base word
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + stages;
-  uint64_t* tmem_full = bars + 2 * stages;
-  uint64_t* tmem_empty = bars + 2 * stages + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = smem + static_cast<size_t>(p.sa) * a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + static_cast<size_t>(p.sb) * b_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + p.sa;
+  uint64_t* b_full = a_empty + p.sa;
+  uint64_t* b_empty = b_full + p.sb;
+  uint64_t* tmem_full = b_empty + p.sb;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int groups = stages >= 4 ? 4 : 2;  // producer warp groups (never more than stages)
+  const int groups = p.sa >= 4 ? 4 : 2;  // producer warp groups (never more than A stages)
 
-  // TMEM columns: two accumulators of n_out fp32 columns, power of two >= 32
+  // TMEM: two sets of T accumulators of n_cta fp32 columns each, power of two >= 32
   uint32_t tmem_cols = 32;
-  while (tmem_cols < static_cast<uint32_t>(2 * n_cta)) tmem_cols <<= 1;
+  while (tmem_cols < static_cast<uint32_t>(2 * T * n_cta)) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), kProducerWarps / groups + 1);  // one producer warp group + the weight loader
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+    for (int s = 0; s < p.sa; ++s) {
+      mbar_init(smem_u32(&a_full[s]), kProducerWarps / groups);
+      mbar_init(smem_u32(&a_empty[s]), 1);
+    }
+    for (int s = 0; s < p.sb; ++s) {
+      mbar_init(smem_u32(&b_full[s]), 1);
+      mbar_init(smem_u32(&b_empty[s]), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tmem_full[a]), 1);
@@ -255,27 +312,28 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p, 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const CtaWork w(p);
 
   if (warp < kProducerWarps) {
     // ================= A producers =================
     if (groups == 4)
-      produce_a<kSplit, 4>(p, stages, stage_base, stage_bytes, full_bar, empty_bar, warp, lane);
+      produce_a<kSplit, 4>(p, w, a_ring, a_full, a_empty, warp, lane);
     else
-      produce_a<kSplit, 2>(p, stages, stage_base, stage_bytes, full_bar, empty_bar, warp, lane);
+      produce_a<kSplit, 2>(p, w, a_ring, a_full, a_empty, warp, lane);
   } else if (warp == kLoaderWarp) {
-    // ================= B loader (TMA bulk copies of the packed weight chunks) =================
+    // ================= B loader: weight chunks through their own ring (TMA bulk copies) =================
+    // A chunk serves all T tiles of the super-tile, and the ring runs ahead of the A stream, so neither the
+    // L2 latency nor the L2 bandwidth of the weights sits on the A-stage turnaround.
     if (lane == 0) {
+      const uint32_t part_bytes = static_cast<uint32_t>(n_cta) * 128u;
       int stage = 0;
       uint32_t phase = 0;
-      constexpr int kParts = Smem<kSplit>::kParts;
-      const uint32_t b_bytes = static_cast<uint32_t>(Smem<kSplit>::b_bytes(n_cta));
-      const uint32_t part_bytes = static_cast<uint32_t>(n_cta) * 128u;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int i = 0; i < w.n_super; ++i) {
         for (int c = 0; c < p.chunks; ++c) {
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-          const uint32_t bar = smem_u32(&full_bar[stage]);
-          mbar_arrive_expect_tx(bar, b_bytes);
-          const uint32_t dst = smem_u32(stage_base + static_cast<size_t>(stage) * stage_bytes + Smem<kSplit>::a_bytes());
+          mbar_wait(smem_u32(&b_empty[stage]), phase ^ 1);
+          const uint32_t bar = smem_u32(&b_full[stage]);
+          mbar_arrive_expect_tx(bar, static_cast<uint32_t>(b_bytes));
+          const uint32_t dst = smem_u32(b_ring + static_cast<size_t>(stage) * b_bytes);
           for (int part = 0; part < kParts; ++part) {
             const uint8_t* src = reinterpret_cast<const uint8_t*>(p.packed) +
                                  (static_cast<size_t>(c * kParts + part) * p.n_out + n0) * 128u;
@@ -284,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p, 
               bulk_g2s(dst + part * part_bytes + o, src + o, n, bar);
             }
           }
-          if (++stage == stages) {
+          if (++stage == p.sb) {
             stage = 0;
             phase ^= 1;
           }
@@ -295,80 +353,88 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p, 
   } else if (warp == kMmaWarp) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase[2] = {0, 0};
       const uint32_t idesc = make_idesc_tf32(kTileM, n_cta);
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase[acc] ^ 1);
+      int sa_ = 0, sb_ = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int i = 0; i < w.n_super; ++i) {
+        const int acc = i & 1;
+        const uint32_t acc_phase = static_cast<uint32_t>((i >> 1) & 1);
+        const int ti = w.tiles_in(p, i);
+        mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * n_cta);
         for (int c = 0; c < p.chunks; ++c) {
-          mbar_wait(smem_u32(&full_bar[stage]), phase);
-          tc_fence_after();
-          const uint32_t a_hi = smem_u32(stage_base + static_cast<size_t>(stage) * stage_bytes);
-          const uint32_t b_hi = a_hi + Smem<kSplit>::a_bytes();
-          const uint64_t da_hi = make_desc_sw128(a_hi);
+          mbar_wait(smem_u32(&b_full[sb_]), pb);
+          const uint32_t b_hi = smem_u32(b_ring + static_cast<size_t>(sb_) * b_bytes);
           const uint64_t db_hi = make_desc_sw128(b_hi);
-          const uint64_t da_lo = make_desc_sw128(a_hi + a_part);
           const uint64_t db_lo = make_desc_sw128(b_hi + b_part);
+          for (int t = 0; t < ti; ++t) {
+            mbar_wait(smem_u32(&a_full[sa_]), pa);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(a_ring + static_cast<size_t>(sa_) * a_bytes);
+            const uint64_t da_hi = make_desc_sw128(a_hi);
+            const uint64_t da_lo = make_desc_sw128(a_hi + a_part);
+            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>((acc * T + t) * n_cta);
 #pragma unroll
-          for (int j = 0; j < kChunkK / 8; ++j) {
-            if (p.debug & 1) break;
-            const uint64_t adv = static_cast<uint64_t>(j * 2);  // 8 tf32 = 32 bytes = 2 x 16 B
-            if (kSplit) {
-              tc_mma_tf32(tmem_d, da_lo + adv, db_hi + adv, idesc, (c | j) ? 1u : 0u);
-              tc_mma_tf32(tmem_d, da_hi + adv, db_lo + adv, idesc, 1u);
-              tc_mma_tf32(tmem_d, da_hi + adv, db_hi + adv, idesc, 1u);
-            } else {
-              tc_mma_tf32(tmem_d, da_hi + adv, db_hi + adv, idesc, (c | j) ? 1u : 0u);
+            for (int j = 0; j < kChunkK / 8; ++j) {
+              if (p.debug & 1) break;
+              const uint64_t adv = static_cast<uint64_t>(j * 2);  // 8 tf32 = 32 bytes = 2 x 16 B
+              if (kSplit) {
+                tc_mma_tf32(tmem_d, da_lo + adv, db_hi + adv, idesc, (c | j) ? 1u : 0u);
+                tc_mma_tf32(tmem_d, da_hi + adv, db_lo + adv, idesc, 1u);
+                tc_mma_tf32(tmem_d, da_hi + adv, db_hi + adv, idesc, 1u);
+              } else {
+                tc_mma_tf32(tmem_d, da_hi + adv, db_hi + adv, idesc, (c | j) ? 1u : 0u);
+              }
+            }
+            tc_commit(smem_u32(&a_empty[sa_]));  // A stage reusable once these MMAs have read it
+            if (++sa_ == p.sa) {
+              sa_ = 0;
+              pa ^= 1;
             }
           }
-          tc_commit(smem_u32(&empty_bar[stage]));  // stage reusable once these MMAs have read it
-          if (++stage == stages) {
-            stage = 0;
-            phase ^= 1;
+          tc_commit(smem_u32(&b_empty[sb_]));    // weight chunk consumed by all tiles of the super-tile
+          if (++sb_ == p.sb) {
+            sb_ = 0;
+            pb ^= 1;
           }
         }
-        tc_commit(smem_u32(&tmem_full[acc]));  // accumulator complete
-        acc_phase[acc] ^= 1;
-        acc ^= 1;
+        tc_commit(smem_u32(&tmem_full[acc]));    // accumulators of the super-tile complete
       }
     }
     __syncwarp();
   } else {
     // ================= epilogue (4 warps; warp w may only touch TMEM lanes 32*(w%4)..+31) =================
     const int quarter = warp & 3;
-    int acc = 0;
-    uint32_t acc_phase[2] = {0, 0};
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      mbar_wait(smem_u32(&tmem_full[acc]), acc_phase[acc]);
+    for (int i = 0; i < w.n_super; ++i) {
+      const int acc = i & 1;
+      const int ti = w.tiles_in(p, i);
+      const int st = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+      mbar_wait(smem_u32(&tmem_full[acc]), static_cast<uint32_t>((i >> 1) & 1));
       tc_fence_after();
-      const int64_t row = static_cast<int64_t>(tile) * kTileM + quarter * 32 + lane;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * n_cta);
-      for (int c0 = 0; c0 < n_cta; c0 += 16) {
-        uint32_t r[16];
-        tc_ld16(taddr + c0, r);
-        tc_wait_ld();
-        if (row < p.num_out) {
-          float* dst = p.out + row * p.n_out + n0 + c0;
+      for (int t = 0; t < ti; ++t) {
+        const int64_t row = (static_cast<int64_t>(st) * T + t) * kTileM + quarter * 32 + lane;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>((acc * T + t) * n_cta);
+        for (int c0 = 0; c0 < n_cta; c0 += 16) {
+          uint32_t r[16];
+          tc_ld16(taddr + c0, r);
+          tc_wait_ld();
+          if (row < p.num_out && !(p.debug & 32)) {
+            float* dst = p.out + row * p.n_out + n0 + c0;
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4 o;
-            o.x = __uint_as_float(r[j + 0]) + (p.bias ? p.bias[n0 + c0 + j + 0] : 0.f);
-            o.y = __uint_as_float(r[j + 1]) + (p.bias ? p.bias[n0 + c0 + j + 1] : 0.f);
-            o.z = __uint_as_float(r[j + 2]) + (p.bias ? p.bias[n0 + c0 + j + 2] : 0.f);
-            o.w = __uint_as_float(r[j + 3]) + (p.bias ? p.bias[n0 + c0 + j + 3] : 0.f);
-            *reinterpret_cast<float4*>(dst + j) = o;
+            for (int j = 0; j < 16; j += 4) {
+              float4 o;
+              o.x = __uint_as_float(r[j + 0]) + (p.bias ? p.bias[n0 + c0 + j + 0] : 0.f);
+              o.y = __uint_as_float(r[j + 1]) + (p.bias ? p.bias[n0 + c0 + j + 1] : 0.f);
+              o.z = __uint_as_float(r[j + 2]) + (p.bias ? p.bias[n0 + c0 + j + 2] : 0.f);
+              o.w = __uint_as_float(r[j + 3]) + (p.bias ? p.bias[n0 + c0 + j + 3] : 0.f);
+              *reinterpret_cast<float4*>(dst + j) = o;
+            }
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
-      acc_phase[acc] ^= 1;
-      acc ^= 1;
     }
   }
 
@@ -722,7 +788,8 @@ static bool wgrad_supported(int c_in, int c_out, int taps) {
 }
 
 static bool supported(int c_red, int n_out, int taps) {
-  return c_red >= 4 && c_red % 4 == 0 && n_out >= 16 && n_out <= 256 && n_out % 16 == 0 && taps >= 1 && taps <= kMaxTaps;
+  const bool n_ok = n_out >= 16 && n_out % 16 == 0 && (n_out <= 256 || (n_out % 256 == 0 && n_out <= 4096));
+  return c_red >= 4 && c_red % 4 == 0 && n_ok && taps >= 1 && taps <= kMaxTaps;
 }
 
 static int chunks_for(int taps, int c_red) { return (taps * c_red + kChunkK - 1) / kChunkK; }
@@ -765,8 +832,10 @@ extern "C" int efgb_spconv_tc_forward(const float* in_feats, int64_t num_in, int
   EFGB_REQUIRE(tc::supported(c_red, n_out, taps), EFGB_EINVAL, "spconv_tc_forward: unsupported shape (c_red=%d n_out=%d taps=%d)",
                c_red, n_out, taps);
   EFGB_REQUIRE(num_in >= 0 && num_out >= 0, EFGB_EINVAL, "spconv_tc_forward: bad sizes");
+  EFGB_REQUIRE(nbr != nullptr || (taps == 1 && num_in >= num_out), EFGB_EINVAL,
+               "spconv_tc_forward: a null rulebook means identity and needs taps == 1");
   if (num_out == 0) return EFGB_OK;
-  EFGB_REQUIRE(packed && nbr && out_feats && (in_feats || num_in == 0), EFGB_EINVAL, "spconv_tc_forward: null pointer");
+  EFGB_REQUIRE(packed && out_feats && (in_feats || num_in == 0), EFGB_EINVAL, "spconv_tc_forward: null pointer");
   EFGB_REQUIRE((reinterpret_cast<uintptr_t>(in_feats) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_feats) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(packed) & 15) == 0,
                EFGB_EINVAL, "spconv_tc_forward: feature / weight pointers must be 16-byte aligned");
@@ -786,30 +855,54 @@ extern "C" int efgb_spconv_tc_forward(const float* in_feats, int64_t num_in, int
     const char* dbg = getenv("EFGB_TC_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
   }
-  const int nbr_bytes = 0;
-  // few tiles (deep levels): split the output channels over grid.y so that all SMs get work
-  int n_split = 1;
-  while (p.num_tiles * n_split * 2 <= kNumSMs && n_out / (n_split * 2) >= 32 && (n_out / (n_split * 2)) % 16 == 0) n_split *= 2;
-  p.n_cta = n_out / n_split;
-  const int stage_bytes = split ? tc::Smem<true>::stage_bytes(p.n_cta) : tc::Smem<false>::stage_bytes(p.n_cta);
-  const int stages = tc::pick_stages(stage_bytes, nbr_bytes);
-  EFGB_REQUIRE(stages >= 2, EFGB_EINVAL, "spconv_tc_forward: tile does not fit shared memory");
-  const size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + nbr_bytes + (2 * stages + 4) * 8 + 16;
-  const dim3 grid(p.num_tiles * n_split < kNumSMs ? p.num_tiles : kNumSMs / n_split, n_split);
+  // N split: wide outputs (dense GEMMs) are cut into 256-column slabs over grid.y
+  int n_split = n_out > 256 ? n_out / 256 : 1;
+  int n_cta = n_out / n_split;
+  // super-tile: T row tiles share each weight chunk (T * n_cta fp32 columns per accumulator set, two sets)
+  int T = 256 / n_cta;
+  if (T > 8) T = 8;
+  if (T < 1) T = 1;
+  // keep at least ~3/4 of the SMs busy; beyond that, sharing weight chunks across more tiles wins (the weight
+  // stream from L2 is the bound for C >= 64)
+  while (T > 1 && ((p.num_tiles + T - 1) / T) * n_split < (kNumSMs * 3) / 4) T >>= 1;
+  if (T == 1) {
+    // few tiles (deep levels): split the output channels further so that all SMs get work
+    while (p.num_tiles * n_split * 2 <= kNumSMs && n_cta / 2 >= 32 && (n_cta / 2) % 16 == 0) {
+      n_split *= 2;
+      n_cta /= 2;
+    }
+  }
+  p.n_cta = n_cta;
+  p.tiles_per_super = T;
+  p.num_super = (p.num_tiles + T - 1) / T;
+  const int parts = split ? 2 : 1;
+  const int a_bytes = parts * tc::kTileM * 128;
+  const int b_bytes = parts * n_cta * 128;
+  p.sb = b_bytes >= 65536 ? 2 : (b_bytes >= 16384 ? 3 : 4);
+  const int budget = 227 * 1024 - 2048;
+  p.sa = (budget - p.sb * b_bytes) / a_bytes;
+  if (p.sa > 6) p.sa = 6;
+  EFGB_REQUIRE(p.sa >= 2, EFGB_EINVAL, "spconv_tc_forward: tile does not fit shared memory");
+  const size_t smem = 1024 + static_cast<size_t>(p.sa) * a_bytes + static_cast<size_t>(p.sb) * b_bytes +
+                      (2 * p.sa + 2 * p.sb + 4) * 8 + 16;
+  int gx = kNumSMs / n_split;
+  if (gx < 1) gx = 1;
+  if (gx > p.num_super) gx = p.num_super;
+  const dim3 grid(gx, n_split);
   if (split) {
     static bool configured = false;
     if (!configured) {
       EFGB_CUDA_OK(cudaFuncSetAttribute(tc::spconv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       configured = true;
     }
-    tc::spconv_tc_kernel<true><<<grid, tc::kThreads, smem, stream>>>(p, stages);
+    tc::spconv_tc_kernel<true><<<grid, tc::kThreads, smem, stream>>>(p);
   } else {
     static bool configured = false;
     if (!configured) {
       EFGB_CUDA_OK(cudaFuncSetAttribute(tc::spconv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       configured = true;
     }
-    tc::spconv_tc_kernel<false><<<grid, tc::kThreads, smem, stream>>>(p, stages);
+    tc::spconv_tc_kernel<false><<<grid, tc::kThreads, smem, stream>>>(p);
   }
   EFGB_LAUNCH_OK("spconv_tc_kernel");
   return EFGB_OK;

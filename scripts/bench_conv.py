@@ -41,7 +41,18 @@ for mode in modes:
         nbytes = 4 * (2 * mo * c + 27 * c * c + 27 * mo)
         flops = 2 * mo * 27 * c * c
         ppr = float((nbr >= 0).sum()) / mo
-        for kind, fn in (("subm fwd", lambda: ops.spconv_tc(feats, w, None, nbr, 0)),
-                         ("subm wgrad", lambda: ops.spconv_tc_wgrad(feats, go, nbr, 27, c, c))):
+        from efg_b200 import _lib
+        L = _lib.lib()
+        split = 1 if mode == "fp32x3" else 0
+        packed = torch.empty(L.efgb_spconv_tc_packed_bytes(27, c, c, split) // 4, dtype=torch.float32, device=dev)
+        L.efgb_spconv_tc_pack(ops._p(w), c, 27, c, 0, split, ops._p(packed), ops._stream())
+        out = torch.empty(mo, c, device=dev)
+        dw = torch.empty(c, 27, c, device=dev)
+        st = ops._stream()
+        def fwd_only():
+            L.efgb_spconv_tc_forward(ops._p(feats), mo, c, ops._p(packed), None, ops._p(nbr), mo, 27, c, split, ops._p(out), st)
+        def wgrad_only():
+            L.efgb_spconv_tc_wgrad(ops._p(feats), mo, c, ops._p(go), ops._p(nbr), mo, 27, c, split, ops._p(dw), st)
+        for kind, fn in (("subm fwd", fwd_only), ("subm wgrad", wgrad_only)):
             us = timeit(fn)
             print("L%d %7d %4d  %-10s %8.1f  %8.1f  %8.1f  %5.1f  [%s]" % (lvl + 1, mo, c, kind, us, nbytes / us / 1e3, flops / us / 1e6, ppr, mode))
