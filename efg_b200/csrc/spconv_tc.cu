@@ -506,7 +506,7 @@ struct WgradParams {
   const int32_t* nbr;   // [num_out, taps]
   float* dw;            // [c_out, taps, c_in], zero-initialised
   int64_t num_out;
-  int c_in, c_out, taps, n_pad;
+  int c_in, c_out, taps, n_pad;   // c_out = full output width (row stride of gout / dW); n_pad = columns per CTA slab
   int groups;           // ceil(taps * c_in / 128)
   int row_chunks;
   int64_t rows_per_chunk;  // multiple of kWgRows
@@ -561,7 +561,8 @@ __device__ __forceinline__ void wgrad_produce(const WgradParams& p, const int st
   constexpr int kPiecesA = (kWgRows * 32) / kGroupThreads;  // 16-byte pieces of the A tile per thread
   const int gidx = warp / kWarpsPerGroup;
   const int tg = (warp % kWarpsPerGroup) * 32 + lane;
-  const int pg = p.n_pad / 4;  // 16-byte pieces per grad_out row (padded)
+  const int pg = p.n_pad / 4;  // 16-byte pieces per grad_out row slab (padded)
+  const int co0 = static_cast<int>(blockIdx.y) * p.n_pad;  // first output channel of this CTA's slab
   const int flat_m = p.taps * p.c_in;
   const int spi = static_cast<int>(p.rows_per_chunk / kWgRows);  // stage slots per item
   const int my_items = (p.num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
@@ -592,7 +593,7 @@ __device__ __forceinline__ void wgrad_produce(const WgradParams& p, const int st
       if (flat < flat_m && row < row_end) {
         const int tap = flat / p.c_in;
         ci_of[i] = flat - tap * p.c_in;
-        src[i] = __ldg(p.nbr + row * p.taps + tap);
+        src[i] = p.nbr ? __ldg(p.nbr + row * p.taps + tap) : static_cast<int32_t>(row);
       }
     }
     float4 va[kPiecesA];
@@ -622,7 +623,8 @@ __device__ __forceinline__ void wgrad_produce(const WgradParams& p, const int st
         if (e < kWgRows * pg) {
           const int r = e / pg, pc = e - r * pg;
           const int64_t row = rb + r;
-          if (row < row_end && pc * 4 < p.c_out) vg[i] = __ldg(reinterpret_cast<const float4*>(p.gout + row * p.c_out + pc * 4));
+          if (row < row_end && co0 + pc * 4 < p.c_out)
+            vg[i] = __ldg(reinterpret_cast<const float4*>(p.gout + row * p.c_out + co0 + pc * 4));
         }
       }
 #pragma unroll
@@ -760,7 +762,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_wgrad_tc_kernel(const Wgra
         if (m_ok) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int co = c0 + j;
+            const int co = static_cast<int>(blockIdx.y) * p.n_pad + c0 + j;
             const float v = __uint_as_float(r[j]);
             if (co < p.c_out && v != 0.f) atomicAdd(p.dw + (static_cast<int64_t>(co) * p.taps + tap) * p.c_in + ci, v);
           }
@@ -784,7 +786,8 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_wgrad_tc_kernel(const Wgra
 
 static bool wgrad_supported(int c_in, int c_out, int taps) {
   const bool cin_ok = c_in >= 16 && c_in % 4 == 0 && ((128 % c_in == 0) || (c_in % 128 == 0));
-  return cin_ok && c_out >= 16 && c_out <= 256 && c_out % 16 == 0 && taps >= 1 && taps <= kMaxTaps;
+  const bool cout_ok = c_out >= 16 && c_out % 16 == 0 && (c_out <= 256 || (c_out % 256 == 0 && c_out <= 4096));
+  return cin_ok && cout_ok && taps >= 1 && taps <= kMaxTaps;
 }
 
 static bool supported(int c_red, int n_out, int taps) {
@@ -919,7 +922,9 @@ extern "C" int efgb_spconv_tc_wgrad(const float* in_feats, int64_t num_in, int c
   EFGB_REQUIRE(num_in >= 0 && num_out >= 0 && dw_param, EFGB_EINVAL, "spconv_tc_wgrad: bad argument");
   EFGB_CUDA_OK(cudaMemsetAsync(dw_param, 0, static_cast<size_t>(c_out) * taps * c_in * sizeof(float), stream));
   if (num_out == 0 || num_in == 0) return EFGB_OK;
-  EFGB_REQUIRE(in_feats && grad_out && nbr, EFGB_EINVAL, "spconv_tc_wgrad: null pointer");
+  EFGB_REQUIRE(in_feats && grad_out, EFGB_EINVAL, "spconv_tc_wgrad: null pointer");
+  EFGB_REQUIRE(nbr != nullptr || (taps == 1 && num_in >= num_out), EFGB_EINVAL,
+               "spconv_tc_wgrad: a null rulebook means identity and needs taps == 1");
   EFGB_REQUIRE((reinterpret_cast<uintptr_t>(in_feats) & 15) == 0 && (reinterpret_cast<uintptr_t>(grad_out) & 15) == 0, EFGB_EINVAL,
                "spconv_tc_wgrad: feature pointers must be 16-byte aligned");
   tc::WgradParams p;
@@ -931,9 +936,10 @@ extern "C" int efgb_spconv_tc_wgrad(const float* in_feats, int64_t num_in, int c
   p.c_in = c_in;
   p.c_out = c_out;
   p.taps = taps;
-  p.n_pad = c_out < 32 ? 32 : (c_out + 31) / 32 * 32;
+  const int n_slabs = c_out > 256 ? c_out / 256 : 1;
+  p.n_pad = c_out > 256 ? 256 : (c_out < 32 ? 32 : (c_out + 31) / 32 * 32);
   p.groups = (taps * c_in + 127) / 128;
-  int64_t chunks = (kNumSMs * 3 + p.groups - 1) / p.groups;
+  int64_t chunks = (kNumSMs * 3 + p.groups * n_slabs - 1) / (p.groups * n_slabs);
   const int64_t max_chunks = (num_out + 255) / 256;
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
@@ -948,7 +954,10 @@ extern "C" int efgb_spconv_tc_wgrad(const float* in_feats, int64_t num_in, int c
   if (stages > 6) stages = 6;
   EFGB_REQUIRE(stages >= 2, EFGB_EINVAL, "spconv_tc_wgrad: tile does not fit shared memory");
   const size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + (2 * stages + 4) * 8 + 16;
-  const int grid = p.num_items < kNumSMs ? p.num_items : kNumSMs;
+  int gx = kNumSMs / n_slabs;
+  if (gx < 1) gx = 1;
+  if (gx > p.num_items) gx = p.num_items;
+  const dim3 grid(gx, n_slabs);
   if (split) {
     static bool configured = false;
     if (!configured) {

@@ -12,6 +12,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from ...backend import cuda_backend
+from ...modeling.norm import TokenLinear
 
 
 class Box3dAttention(nn.Module):
@@ -33,8 +34,8 @@ class Box3dAttention(nn.Module):
         self.linear_box_bias = nn.Parameter(torch.zeros(num_head * num_level * self.num_variable))
         self.linear_attn_weight = nn.Parameter(torch.zeros(num_head * num_level * self.num_point, d_model))
         self.linear_attn_bias = nn.Parameter(torch.zeros(num_head * num_level * self.num_point))
-        self.value_proj = nn.Linear(d_model, d_model)
-        self.out_proj = nn.Linear(d_model, d_model)
+        self.value_proj = TokenLinear(d_model, d_model, backend=self._backend[0])
+        self.out_proj = TokenLinear(d_model, d_model, backend=self._backend[0])
 
         # grid of kernel offsets in units of the box size: (x, y) pairs, x fastest
         if kernel_size % 2 == 0:

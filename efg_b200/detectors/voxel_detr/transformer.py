@@ -8,6 +8,8 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from ...backend import cuda_backend
+from ...modeling.norm import TokenLinear
 from .box_attention import Box3dAttention
 
 
@@ -42,9 +44,9 @@ class TransformerEncoderLayer(nn.Module):
     def __init__(self, d_model, nhead, nlevel, dim_feedforward, dropout, activation, backend=None):
         super().__init__()
         self.self_attn = Box3dAttention(d_model, nlevel, nhead, with_rotation=False, backend=backend)
-        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.linear1 = TokenLinear(d_model, dim_feedforward, backend=backend or cuda_backend())
         self.dropout = nn.Dropout(dropout)
-        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.linear2 = TokenLinear(dim_feedforward, d_model, backend=backend or cuda_backend())
         self.norm1 = nn.LayerNorm(d_model)
         self.norm2 = nn.LayerNorm(d_model)
         self.dropout1 = nn.Dropout(dropout)

@@ -35,3 +35,22 @@ def get_activation(activation):
     if atype in ("GELU",):
         return table[atype]()
     return table[atype](inplace=inplace)
+
+
+class TokenLinear(nn.Linear):
+    """nn.Linear (same parameters / state_dict) whose forward runs on the tcgen05 gather-GEMM kernels with an
+    identity rulebook when the input has many rows (the 70k-token linears of the box-attention encoder) and
+    the module belongs to the CUDA backend; otherwise plain F.linear (cuBLAS / CPU)."""
+
+    def __init__(self, in_features, out_features, bias=True, backend=None):
+        super().__init__(in_features, out_features, bias=bias)
+        self._tc = backend is not None and getattr(backend, "name", "") == "efgb200-cuda"
+
+    def forward(self, x):
+        if self._tc and x.is_cuda and x.dtype == self.weight.dtype:
+            from .. import ops
+
+            rows = x.numel() // x.shape[-1]
+            if ops.dense_linear_supported(rows, self.in_features, self.out_features):
+                return ops.dense_linear(x, self.weight, self.bias)
+        return nn.functional.linear(x, self.weight, self.bias)

@@ -283,17 +283,21 @@ def spconv_tc(feats, w_param, bias, nbr, mode):
     2 dgrad-submanifold; feats [Mi, c_red]; returns [nbr.shape[0], N]."""
     _check(feats, "features", torch.float32)
     _check(w_param, "weight", torch.float32)
-    _check(nbr, "rulebook", torch.int32)
     c_out, taps, c_in = w_param.shape
     n_out, c_red = (c_out, c_in) if mode == 0 else (c_in, c_out)
-    if feats.shape[1] != c_red or nbr.shape[1] != taps:
-        raise RuntimeError("spconv_tc: shape mismatch feats %r weight %r rulebook %r mode %d" %
-                           (tuple(feats.shape), tuple(w_param.shape), tuple(nbr.shape), mode))
+    if nbr is None:  # identity rulebook: a dense GEMM out = feats @ W^T (taps == 1)
+        if taps != 1:
+            raise RuntimeError("spconv_tc: an identity rulebook needs a 1-tap weight")
+    else:
+        _check(nbr, "rulebook", torch.int32)
+    if feats.shape[1] != c_red or (nbr is not None and nbr.shape[1] != taps):
+        raise RuntimeError("spconv_tc: shape mismatch feats %r weight %r mode %d" %
+                           (tuple(feats.shape), tuple(w_param.shape), mode))
     split = 1 if CONV_PRECISION == "fp32x3" else 0
     L = _lib.lib()
     dev = feats.device
     packed = torch.empty(L.efgb_spconv_tc_packed_bytes(taps, c_red, n_out, split) // 4, dtype=torch.float32, device=dev)
-    m_out = nbr.shape[0]
+    m_out = nbr.shape[0] if nbr is not None else feats.shape[0]
     out = torch.empty((m_out, n_out), dtype=torch.float32, device=dev)
     t0 = PROFILER.begin() if PROFILER is not None else None
     _lib.check(L.efgb_spconv_tc_pack(_p(w_param), c_out, taps, c_in, mode, split, _p(packed), _stream()), "spconv_tc_pack")
@@ -306,8 +310,9 @@ def spconv_tc(feats, w_param, bias, nbr, mode):
                                   split, _p(out), _stream())
     _lib.check(rc, "spconv_tc_forward")
     if t0 is not None:
-        nbytes = 4 * (feats.shape[0] * c_red + m_out * n_out + taps * c_red * n_out + taps * m_out)
-        PROFILER.end("spconv_tc_c%d" % max(c_red, n_out), t0, nbytes, 2 * m_out * taps * c_red * n_out)
+        nbytes = 4 * (feats.shape[0] * c_red + m_out * n_out + taps * c_red * n_out + (taps * m_out if nbr is not None else 0))
+        fam = ("spconv_tc_c%d" % max(c_red, n_out)) if nbr is not None else "dense_tc_gemm"
+        PROFILER.end(fam, t0, nbytes, 2 * m_out * taps * c_red * n_out)
     return out
 
 
@@ -319,19 +324,63 @@ def spconv_tc_wgrad(feats, grad_out, nbr, taps, c_in, c_out):
     """Tensor-core wgrad; returns dW in the reference parameter layout [c_out, taps, c_in]."""
     _check(feats, "features", torch.float32)
     _check(grad_out, "grad_out", torch.float32)
-    _check(nbr, "rulebook", torch.int32)
+    if nbr is not None:
+        _check(nbr, "rulebook", torch.int32)
+    m_out = nbr.shape[0] if nbr is not None else grad_out.shape[0]
     dw = torch.empty((c_out, taps, c_in), dtype=torch.float32, device=feats.device)
     L = _lib.lib()
     split = 1 if CONV_PRECISION == "fp32x3" else 0
     t0 = PROFILER.begin() if PROFILER is not None else None
-    rc = L.efgb_spconv_tc_wgrad(_p(feats), feats.shape[0], c_in, _p(grad_out), _p(nbr), nbr.shape[0], taps, c_out, split,
+    rc = L.efgb_spconv_tc_wgrad(_p(feats), feats.shape[0], c_in, _p(grad_out), _p(nbr), m_out, taps, c_out, split,
                                 _p(dw), _stream())
     _lib.check(rc, "spconv_tc_wgrad")
     if t0 is not None:
-        m_out = nbr.shape[0]
-        nbytes = 4 * (feats.shape[0] * c_in + m_out * c_out + taps * c_in * c_out + taps * m_out)
-        PROFILER.end("spconv_tc_wgrad_c%d" % max(c_in, c_out), t0, nbytes, 2 * m_out * taps * c_in * c_out)
+        nbytes = 4 * (feats.shape[0] * c_in + m_out * c_out + taps * c_in * c_out + (taps * m_out if nbr is not None else 0))
+        fam = ("spconv_tc_wgrad_c%d" % max(c_in, c_out)) if nbr is not None else "dense_tc_wgrad"
+        PROFILER.end(fam, t0, nbytes, 2 * m_out * taps * c_in * c_out)
     return dw
+
+
+class _DenseLinearFn(torch.autograd.Function):
+    """y = x @ W^T + b on the tensor-core gather-GEMM kernels with an identity rulebook (a dense layer is a
+    1-tap sparse conv over all rows).  fp32-faithful in "fp32x3" mode; used for the large token-wise linears
+    of the box-attention encoder (M = B * 35 344 rows)."""
+
+    @staticmethod
+    def forward(ctx, x2d, weight, bias):
+        x2d = x2d.contiguous()
+        w3 = weight.contiguous().view(weight.shape[0], 1, weight.shape[1])
+        ctx.save_for_backward(x2d, w3)
+        ctx.has_bias = bias is not None
+        return spconv_tc(x2d, w3, bias, None, 0)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x2d, w3 = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        c_out, _, c_in = w3.shape
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = spconv_tc(grad_out, w3, None, None, 1)
+        if ctx.needs_input_grad[1]:
+            dw = spconv_tc_wgrad(x2d, grad_out, None, 1, c_in, c_out).view(c_out, c_in)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = grad_out.sum(0)
+        return dx, dw, db
+
+
+def dense_linear_supported(rows, c_in, c_out):
+    L = _lib.lib()
+    return (CONV_PRECISION != "simt" and rows >= 4096 and c_in >= 16 and
+            bool(L.efgb_spconv_tc_supported(c_in, c_out, 1)) and bool(L.efgb_spconv_tc_supported(c_out, c_in, 1)) and
+            bool(L.efgb_spconv_tc_wgrad_supported(c_in, c_out, 1)))
+
+
+def dense_linear(x, weight, bias=None):
+    """torch.nn.functional.linear for CUDA tensors with many rows, on the tcgen05 kernels."""
+    lead = x.shape[:-1]
+    y = _DenseLinearFn.apply(x.reshape(-1, x.shape[-1]), weight, bias)
+    return y.view(*lead, weight.shape[0])
 
 
 def spconv_wgrad(feats, grad_out, nbr, taps, c_in, c_out):

@@ -131,3 +131,29 @@ def test_tc_wgrad_vs_oracle(precision, mode, tol, cin, cout, m, ksize):
     scale = max(1.0, float(exp.abs().max()))
     err = (dw.cpu() - exp).abs().max().item()
     assert err < tol * scale, (mode, cin, cout, m, err, scale)
+
+
+@pytest.mark.parametrize("cin,cout", [(256, 256), (256, 1024), (1024, 256), (256, 32)])
+def test_dense_linear_on_tensor_cores_vs_torch_fp64(precision, cin, cout):
+    """The token-wise linears of the box-attention encoder routed through the tcgen05 kernels (identity
+    rulebook): forward, dgrad, wgrad and bias grad vs float64 torch."""
+    ops = precision
+    ops.CONV_PRECISION = "fp32x3"
+    torch.manual_seed(cin + cout)
+    m = 9000
+    x = torch.randn(m, cin, device="cuda")
+    lin = torch.nn.Linear(cin, cout).cuda()
+    assert ops.dense_linear_supported(m, cin, cout)
+    xg = x.clone().requires_grad_(True)
+    y = ops.dense_linear(xg.view(3, m // 3, cin), lin.weight, lin.bias)
+    assert y.shape == (3, m // 3, cout)
+    go = torch.randn_like(y)
+    y.backward(go)
+    xd = x.double().requires_grad_(True)
+    wd, bd = lin.weight.detach().double().requires_grad_(True), lin.bias.detach().double().requires_grad_(True)
+    yd = torch.nn.functional.linear(xd, wd, bd)
+    yd.backward(go.view(m, cout).double())
+    assert (y.view(m, cout).double() - yd).abs().max().item() < 2e-4
+    assert (xg.grad.double() - xd.grad).abs().max().item() < 2e-4 * max(1.0, xd.grad.abs().max().item())
+    assert (lin.weight.grad.double() - wd.grad).abs().max().item() < 5e-4 * max(1.0, wd.grad.abs().max().item())
+    assert (lin.bias.grad.double() - bd.grad).abs().max().item() < 1e-3 * max(1.0, bd.grad.abs().max().item())
