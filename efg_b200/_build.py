@@ -81,7 +81,11 @@ def build(verbose=False, force=False):
                 sys.stderr.write(log)
     newest = max(os.path.getmtime(o) for o in objs)
     if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < newest:
-        cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+        # shared cudart: the library must use the SAME runtime instance as PyTorch (already loaded in the process)
+        # so that stream capture (CUDA graphs) sees one consistent runtime; rpath is the fallback when torch is
+        # not imported first
+        cmd = [nvcc, "-shared", "-cudart", "shared", "-o", LIB_PATH] + objs + [
+            "-gencode", "arch=compute_100a,code=sm_100a", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

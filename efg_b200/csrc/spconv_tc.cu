@@ -602,6 +602,25 @@ __device__ __forceinline__ void wgrad_produce(const WgradParams& p, const int st
       va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (src[i] >= 0) va[i] = __ldg(reinterpret_cast<const float4*>(p.in + static_cast<int64_t>(src[i]) * p.c_in + ci_of[i]));
     }
+    // grad_out rows: the first batch of loads is issued together with the A gathers (one memory latency for the
+    // whole stage instead of one per batch); wider slabs need further batches
+    constexpr int kBatch = 8;
+    const int g_total = kWgRows * pg;
+    float4 vg[kBatch];
+    auto load_g = [&](int e0) {
+#pragma unroll
+      for (int i = 0; i < kBatch; ++i) {
+        const int e = e0 + i * kGroupThreads + tg;
+        vg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < g_total) {
+          const int r = e / pg, pc = e - r * pg;
+          const int64_t row = rb + r;
+          if (row < row_end && co0 + pc * 4 < p.c_out)
+            vg[i] = __ldg(reinterpret_cast<const float4*>(p.gout + row * p.c_out + co0 + pc * 4));
+        }
+      }
+    };
+    load_g(0);
     mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
     uint8_t* a_hi = smem + static_cast<size_t>(stage) * stage_bytes;
     uint8_t* a_lo = a_hi + a_part;
@@ -613,24 +632,12 @@ __device__ __forceinline__ void wgrad_produce(const WgradParams& p, const int st
       const int r = e >> 5, pc = e & 31;
       split_store(a_hi, a_lo, static_cast<uint32_t>(pc >> 3) * (kWgRows * 128) + mn_piece_offset(r, pc), va[i], kSplit);
     }
-    // ---- G: 32 rows x pg pieces, 8 per thread per pass
-    for (int e0 = 0; e0 < kWgRows * pg; e0 += kGroupThreads * 8) {
-      float4 vg[8];
+    for (int e0 = 0; e0 < g_total; e0 += kGroupThreads * kBatch) {
+      if (e0 > 0) load_g(e0);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < kBatch; ++i) {
         const int e = e0 + i * kGroupThreads + tg;
-        vg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e < kWgRows * pg) {
-          const int r = e / pg, pc = e - r * pg;
-          const int64_t row = rb + r;
-          if (row < row_end && co0 + pc * 4 < p.c_out)
-            vg[i] = __ldg(reinterpret_cast<const float4*>(p.gout + row * p.c_out + co0 + pc * 4));
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int e = e0 + i * kGroupThreads + tg;
-        if (e < kWgRows * pg) {
+        if (e < g_total) {
           const int r = e / pg, pc = e - r * pg;
           split_store(g_hi, g_lo, static_cast<uint32_t>(pc >> 3) * (kWgRows * 128) + mn_piece_offset(r, pc), vg[i], kSplit);
         }
@@ -936,8 +943,10 @@ extern "C" int efgb_spconv_tc_wgrad(const float* in_feats, int64_t num_in, int c
   p.c_in = c_in;
   p.c_out = c_out;
   p.taps = taps;
-  const int n_slabs = c_out > 256 ? c_out / 256 : 1;
-  p.n_pad = c_out > 256 ? 256 : (c_out < 32 ? 32 : (c_out + 31) / 32 * 32);
+  // output-channel slabs of at most kSlab columns per CTA (128-column slabs were measured slower: more re-reads of A)
+  const int kSlab = 256;
+  const int n_slabs = c_out > kSlab ? c_out / kSlab : 1;
+  p.n_pad = c_out > kSlab ? kSlab : (c_out < 32 ? 32 : (c_out + 31) / 32 * 32);
   p.groups = (taps * c_in + 127) / 128;
   int64_t chunks = (kNumSMs * 3 + p.groups * n_slabs - 1) / (p.groups * n_slabs);
   const int64_t max_chunks = (num_out + 255) / 256;
