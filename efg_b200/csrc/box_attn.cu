@@ -294,3 +294,144 @@ extern "C" int efgb_box_attn_backward(const float* value, const int64_t* spatial
   EFGB_LAUNCH_OK("box_attn_bwd_kernel");
   return EFGB_OK;
 }
+
+// =================================================================================================
+// Fused sampling-grid + attention-softmax ("where to attend"), forward and backward.
+//
+// Reference: Box3dAttention._where_to_attend and the softmax in Box3dAttention.forward
+// (VD/modules/box_attention.py:62-95, :105-108), ~20 separate elementwise / reduction kernels over
+// [B, LQ, H, L, 25, 2] tensors there.  One warp per (b, q, h): lane p < P owns sampling point p of every level.
+//   offsets [B, LQ, H, L, NV]  (NV = 4: dx, dy, dw, dl;  NV = 5: + rotation)     from the box linear layer
+//   logits  [B, LQ, H, L*P]                                                      from the attention linear layer
+//   ref     [B, LQ, 7]  reference windows (cx, cy, cz, w, l, h, angle), no gradient
+//   kidx    [P, 2]      kernel offsets in units of the box size (x, y)
+//   box    = (cx + dx/8*w, cy + dy/8*l, w + dw/8*w, l + dl/8*l);  angle = NV == 5 ? (ref_angle + rot/16)*2pi : ref_angle
+//   g      = kidx[p] * relu(size);  loc[p] = centre + (g.x*cos - g.y*sin, g.x*sin + g.y*cos)
+//   attn   = softmax over all L*P logits of the (b, q, h)
+// =================================================================================================
+namespace efgb {
+
+constexpr float kTwoPi = 6.283185307179586f;
+
+template <bool kBackward>
+__global__ void __launch_bounds__(256)
+box_grid_softmax_kernel(const float* __restrict__ offsets, const float* __restrict__ logits, const float* __restrict__ ref,
+                        const float* __restrict__ kidx, int64_t num_warps, int num_heads, int num_levels, int num_points,
+                        int nv, float* __restrict__ loc, float* __restrict__ attn, const float* __restrict__ g_loc,
+                        const float* __restrict__ g_attn, float* __restrict__ g_offsets, float* __restrict__ g_logits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (idx >= num_warps) return;
+  const int64_t bq = idx / num_heads;
+  const float* r = ref + bq * 7;
+  const float cx = r[0], cy = r[1], w = r[3], l = r[4], ref_angle = r[6];
+  const int lp = num_levels * num_points;
+  const float* lg = logits + idx * lp;
+
+  // ---- softmax over L*P logits (each lane strides over them)
+  float m = -INFINITY;
+  for (int e = lane; e < lp; e += 32) m = fmaxf(m, lg[e]);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+  float s = 0.f;
+  for (int e = lane; e < lp; e += 32) s += expf(lg[e] - m);
+  s = warp_sum(s);
+  const float inv = 1.f / s;
+  if (!kBackward) {
+    for (int e = lane; e < lp; e += 32) attn[idx * lp + e] = expf(lg[e] - m) * inv;
+  } else {
+    float dot = 0.f;
+    for (int e = lane; e < lp; e += 32) dot += expf(lg[e] - m) * inv * g_attn[idx * lp + e];
+    dot = warp_sum(dot);
+    for (int e = lane; e < lp; e += 32) {
+      const float a = expf(lg[e] - m) * inv;
+      g_logits[idx * lp + e] = a * (g_attn[idx * lp + e] - dot);
+    }
+  }
+
+  // ---- sampling grid
+  for (int lvl = 0; lvl < num_levels; ++lvl) {
+    const float* off = offsets + (idx * num_levels + lvl) * nv;
+    const float o0 = off[0], o1 = off[1], o2 = off[2], o3 = off[3];
+    const float bx = cx + o0 / 8.f * w, by = cy + o1 / 8.f * l;
+    const float sw = w + o2 / 8.f * w, sl = l + o3 / 8.f * l;
+    const float angle = nv == 5 ? (ref_angle + off[4] / 16.f) * kTwoPi : ref_angle;
+    float sn, cs;
+    sincosf(angle, &sn, &cs);
+    const float rw = fmaxf(sw, 0.f), rl = fmaxf(sl, 0.f);
+    float a_cx = 0.f, a_cy = 0.f, a_sw = 0.f, a_sl = 0.f, a_ang = 0.f;
+    for (int p0 = 0; p0 < num_points; p0 += 32) {
+      const int p = p0 + lane;
+      if (p < num_points) {
+        const float kx = kidx[2 * p], ky = kidx[2 * p + 1];
+        const float gx = kx * rw, gy = ky * rl;
+        const int64_t o = ((idx * num_levels + lvl) * num_points + p) * 2;
+        if (!kBackward) {
+          *reinterpret_cast<float2*>(loc + o) = make_float2(bx + (gx * cs - gy * sn), by + (gx * sn + gy * cs));
+        } else {
+          const float2 g = *reinterpret_cast<const float2*>(g_loc + o);
+          a_cx += g.x;
+          a_cy += g.y;
+          const float ggx = g.x * cs + g.y * sn;   // d loss / d gx
+          const float ggy = -g.x * sn + g.y * cs;  // d loss / d gy
+          a_sw += ggx * kx;
+          a_sl += ggy * ky;
+          a_ang += g.x * (-gx * sn - gy * cs) + g.y * (gx * cs - gy * sn);
+        }
+      }
+    }
+    if (kBackward) {
+      a_cx = warp_sum(a_cx);
+      a_cy = warp_sum(a_cy);
+      a_sw = warp_sum(a_sw);
+      a_sl = warp_sum(a_sl);
+      a_ang = warp_sum(a_ang);
+      if (lane == 0) {
+        float* go = g_offsets + (idx * num_levels + lvl) * nv;
+        go[0] = a_cx * w / 8.f;
+        go[1] = a_cy * l / 8.f;
+        go[2] = (sw > 0.f ? a_sw : 0.f) * w / 8.f;
+        go[3] = (sl > 0.f ? a_sl : 0.f) * l / 8.f;
+        if (nv == 5) go[4] = a_ang * kTwoPi / 16.f;
+      }
+    }
+  }
+}
+
+}  // namespace efgb
+
+extern "C" int efgb_box_grid_softmax_forward(const float* offsets, const float* logits, const float* ref_windows,
+                                             const float* kernel_indices, int64_t num_bq, int num_heads, int num_levels,
+                                             int num_points, int num_variables, float* loc, float* attn,
+                                             efgb_stream_t stream_) {
+  cudaStream_t stream = as_stream(stream_);
+  EFGB_REQUIRE(num_bq >= 0 && num_heads >= 1 && num_levels >= 1 && num_points >= 1 && (num_variables == 4 || num_variables == 5),
+               EFGB_EINVAL, "box_grid_softmax_forward: bad shape");
+  const int64_t nw = num_bq * num_heads;
+  if (nw == 0) return EFGB_OK;
+  EFGB_REQUIRE(offsets && logits && ref_windows && kernel_indices && loc && attn, EFGB_EINVAL, "box_grid_softmax_forward: null pointer");
+  box_grid_softmax_kernel<false><<<static_cast<unsigned>((nw + 7) / 8), 256, 0, stream>>>(
+      offsets, logits, ref_windows, kernel_indices, nw, num_heads, num_levels, num_points, num_variables, loc, attn, nullptr,
+      nullptr, nullptr, nullptr);
+  EFGB_LAUNCH_OK("box_grid_softmax_kernel<fwd>");
+  return EFGB_OK;
+}
+
+extern "C" int efgb_box_grid_softmax_backward(const float* offsets, const float* logits, const float* ref_windows,
+                                              const float* kernel_indices, const float* grad_loc, const float* grad_attn,
+                                              int64_t num_bq, int num_heads, int num_levels, int num_points,
+                                              int num_variables, float* grad_offsets, float* grad_logits,
+                                              efgb_stream_t stream_) {
+  cudaStream_t stream = as_stream(stream_);
+  EFGB_REQUIRE(num_bq >= 0 && num_heads >= 1 && num_levels >= 1 && num_points >= 1 && (num_variables == 4 || num_variables == 5),
+               EFGB_EINVAL, "box_grid_softmax_backward: bad shape");
+  const int64_t nw = num_bq * num_heads;
+  if (nw == 0) return EFGB_OK;
+  EFGB_REQUIRE(offsets && logits && ref_windows && kernel_indices && grad_loc && grad_attn && grad_offsets && grad_logits, EFGB_EINVAL,
+               "box_grid_softmax_backward: null pointer");
+  box_grid_softmax_kernel<true><<<static_cast<unsigned>((nw + 7) / 8), 256, 0, stream>>>(
+      offsets, logits, ref_windows, kernel_indices, nw, num_heads, num_levels, num_points, num_variables, nullptr, nullptr,
+      grad_loc, grad_attn, grad_offsets, grad_logits);
+  EFGB_LAUNCH_OK("box_grid_softmax_kernel<bwd>");
+  return EFGB_OK;
+}

@@ -88,8 +88,19 @@ class Box3dAttention(nn.Module):
             value = value.masked_fill(v_mask[..., None], float(0))
         value = value.view(B, LV, self.num_head, self.head_dim)
         attn = F.linear(query, self.linear_attn_weight, self.linear_attn_bias)
-        attn = F.softmax(attn.view(B, LQ, self.num_head, -1), dim=-1)
-        attn = attn.view(B, LQ, self.num_head, self.num_level, self.kernel_size, self.kernel_size)
-        grid = self._where_to_attend(query, v_valid_ratios, ref_windows)
+        if (self._backend[0].name == "efgb200-cuda" and query.is_cuda and v_valid_ratios is None and
+                ref_windows.dim() == 3 and ref_windows.shape[-1] == 7):
+            # fused sampling grid + softmax (csrc/box_attn.cu), same math as the branch below
+            from ... import ops
+
+            offsets = F.linear(query, self.linear_box_weight, self.linear_box_bias)
+            grid, attn = ops.BoxGridSoftmaxFunction.apply(
+                offsets.view(B, LQ, self.num_head, self.num_level, self.num_variable),
+                attn.view(B, LQ, self.num_head, -1), ref_windows, self.kernel_indices)
+            attn = attn.view(B, LQ, self.num_head, self.num_level, self.kernel_size, self.kernel_size)
+        else:
+            attn = F.softmax(attn.view(B, LQ, self.num_head, -1), dim=-1)
+            attn = attn.view(B, LQ, self.num_head, self.num_level, self.kernel_size, self.kernel_size)
+            grid = self._where_to_attend(query, v_valid_ratios, ref_windows)
         out = self._backend[0].box_attn(value, v_shape, v_start_index, grid, attn, self.im2col_step)
         return self.out_proj(out), attn

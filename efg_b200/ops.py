@@ -475,3 +475,48 @@ def box_attn_backward(value, shapes, level_start, loc, attn, grad_out):
         nbytes = 4 * (2 * value.numel() + 2 * loc.numel() + 2 * attn.numel() + grad_out.numel())
         PROFILER.end("box_attn_bwd", t0, nbytes, 6 * b * lq * h * nl * npnt * 4 * ch)
     return grad_value, grad_loc, grad_attn
+
+
+class BoxGridSoftmaxFunction(torch.autograd.Function):
+    """(offsets [B,LQ,H,L,NV], logits [B,LQ,H,L*P], ref_windows [B,LQ,7], kernel_indices [P,2]) ->
+    (sampling locations [B,LQ,H,L,P,2], softmax attention [B,LQ,H,L*P]) in one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, offsets, logits, ref_windows, kernel_indices):
+        offsets, logits = offsets.contiguous(), logits.contiguous()
+        ref_windows, kernel_indices = ref_windows.contiguous(), kernel_indices.contiguous()
+        for t, n in ((offsets, "offsets"), (logits, "logits"), (ref_windows, "ref_windows"), (kernel_indices, "kernel_indices")):
+            _check(t, n, torch.float32)
+        b, lq, h, nl, nv = offsets.shape
+        npnt = kernel_indices.shape[0]
+        if logits.shape != (b, lq, h, nl * npnt) or ref_windows.shape != (b, lq, 7):
+            raise RuntimeError("box_grid_softmax: inconsistent shapes %r %r %r" %
+                               (tuple(offsets.shape), tuple(logits.shape), tuple(ref_windows.shape)))
+        loc = torch.empty((b, lq, h, nl, npnt, 2), dtype=torch.float32, device=offsets.device)
+        attn = torch.empty_like(logits)
+        L = _lib.lib()
+        t0 = PROFILER.begin() if PROFILER is not None else None
+        _lib.check(L.efgb_box_grid_softmax_forward(_p(offsets), _p(logits), _p(ref_windows), _p(kernel_indices), b * lq, h, nl,
+                                                   npnt, nv, _p(loc), _p(attn), _stream()), "box_grid_softmax_forward")
+        if t0 is not None:
+            PROFILER.end("box_grid_softmax_fwd", t0, 4 * (offsets.numel() + 2 * logits.numel() + loc.numel()))
+        ctx.save_for_backward(offsets, logits, ref_windows, kernel_indices)
+        return loc, attn
+
+    @staticmethod
+    def backward(ctx, g_loc, g_attn):
+        offsets, logits, ref_windows, kernel_indices = ctx.saved_tensors
+        b, lq, h, nl, nv = offsets.shape
+        npnt = kernel_indices.shape[0]
+        g_loc = g_loc.contiguous() if g_loc is not None else torch.zeros((b, lq, h, nl, npnt, 2), device=offsets.device)
+        g_attn = g_attn.contiguous() if g_attn is not None else torch.zeros_like(logits)
+        g_off = torch.empty_like(offsets)
+        g_log = torch.empty_like(logits)
+        L = _lib.lib()
+        t0 = PROFILER.begin() if PROFILER is not None else None
+        _lib.check(L.efgb_box_grid_softmax_backward(_p(offsets), _p(logits), _p(ref_windows), _p(kernel_indices), _p(g_loc),
+                                                    _p(g_attn), b * lq, h, nl, npnt, nv, _p(g_off), _p(g_log), _stream()),
+                   "box_grid_softmax_backward")
+        if t0 is not None:
+            PROFILER.end("box_grid_softmax_bwd", t0, 4 * (2 * offsets.numel() + 3 * logits.numel() + g_loc.numel()))
+        return g_off, g_log, None, None

@@ -212,6 +212,24 @@ int efgb_box_attn_backward(const float* value, const int64_t* spatial_shapes,
                            float* grad_value, float* grad_loc, float* grad_attn,
                            efgb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused "where to attend" + attention softmax of Box3dAttention
+ * (VD/modules/box_attention.py:62-95 _where_to_attend, :105-108 softmax): from the box-offset and
+ * attention-logit projections of every (batch*query, head) produce the sampling locations
+ * loc [BQ, H, L, P, 2] and the softmax weights attn [BQ, H, L*P] that efgb_box_attn_* consume.
+ *   offsets [BQ, H, L, NV] (NV = 4, or 5 with rotation), logits [BQ, H, L*P], ref_windows [BQ, 7]
+ *   (cx, cy, cz, w, l, h, angle; no gradient), kernel_indices [P, 2].
+ * ------------------------------------------------------------------------------------------ */
+int efgb_box_grid_softmax_forward(const float* offsets, const float* logits, const float* ref_windows,
+                                  const float* kernel_indices, int64_t num_bq, int num_heads,
+                                  int num_levels, int num_points, int num_variables, float* loc,
+                                  float* attn, efgb_stream_t stream);
+int efgb_box_grid_softmax_backward(const float* offsets, const float* logits, const float* ref_windows,
+                                   const float* kernel_indices, const float* grad_loc,
+                                   const float* grad_attn, int64_t num_bq, int num_heads, int num_levels,
+                                   int num_points, int num_variables, float* grad_offsets,
+                                   float* grad_logits, efgb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -101,3 +101,38 @@ def test_box_attn_im2col_contract():
     with pytest.raises(RuntimeError):
         _C.box_attn_forward(v, shapes, start, loc, attn, 2)  # 3 % 2 != 0
     assert _C.box_attn_forward(v, shapes, start, loc, attn, 64).shape == (3, 5, 16)
+
+
+@pytest.mark.parametrize("with_rotation", [False, True])
+def test_fused_grid_softmax_matches_torch_chain(with_rotation):
+    """The fused sampling-grid + softmax kernel vs the reference's chain of torch ops
+    (Box3dAttention._where_to_attend + F.softmax), forward and gradients, 1e-5."""
+    from efg_b200 import ops
+    from efg_b200.detectors.voxel_detr.box_attention import Box3dAttention
+    from oracle.backend_cpu import cpu_backend
+
+    torch.manual_seed(4)
+    B, LQ, d, H = 2, 700, 256, 8
+    mod = Box3dAttention(d, 1, H, with_rotation=with_rotation, backend=cpu_backend()).cuda()  # torch-chain branch
+    with torch.no_grad():
+        mod.linear_box_weight.normal_(0, 0.2)
+        mod.linear_attn_weight.normal_(0, 0.2)
+    query = torch.randn(B, LQ, d, device="cuda")
+    ref = torch.rand(B, LQ, 7, device="cuda")
+    ref[..., 3:5] = ref[..., 3:5] * 0.1 + 0.01
+    # reference chain
+    q1 = query.clone().requires_grad_(True)
+    attn1 = torch.softmax(torch.nn.functional.linear(q1, mod.linear_attn_weight, mod.linear_attn_bias).view(B, LQ, H, -1), -1)
+    grid1 = mod._where_to_attend(q1, None, ref)
+    g_grid, g_attn = torch.randn_like(grid1), torch.randn_like(attn1)
+    (grid1 * g_grid).sum().add((attn1 * g_attn).sum()).backward()
+    # fused
+    q2 = query.clone().requires_grad_(True)
+    offsets = torch.nn.functional.linear(q2, mod.linear_box_weight, mod.linear_box_bias).view(B, LQ, H, 1, mod.num_variable)
+    logits = torch.nn.functional.linear(q2, mod.linear_attn_weight, mod.linear_attn_bias).view(B, LQ, H, -1)
+    grid2, attn2 = ops.BoxGridSoftmaxFunction.apply(offsets, logits, ref, mod.kernel_indices)
+    (grid2 * g_grid).sum().add((attn2 * g_attn).sum()).backward()
+    assert grid2.shape == grid1.shape
+    assert (grid2 - grid1).abs().max().item() < 1e-5
+    assert (attn2 - attn1).abs().max().item() < 1e-6
+    assert (q2.grad - q1.grad).abs().max().item() < 1e-4 * max(1.0, q1.grad.abs().max().item())
