@@ -18,7 +18,9 @@ class MLP(nn.Module):
         super().__init__()
         self.num_layers = num_layers
         dims = [input_dim] + [hidden_dim] * (num_layers - 1) + [output_dim]
-        self.layers = nn.ModuleList(nn.Linear(a, b) for a, b in zip(dims[:-1], dims[1:]))
+        # TokenLinear == nn.Linear (same parameters); with many rows (the proposal head runs on all 70k BEV
+        # tokens) CUDA inputs go through the tcgen05 dense path, small inputs stay on cuBLAS
+        self.layers = nn.ModuleList(TokenLinear(a, b, backend=cuda_backend()) for a, b in zip(dims[:-1], dims[1:]))
 
     def forward(self, x):
         for i, layer in enumerate(self.layers):
