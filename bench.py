@@ -50,6 +50,9 @@ def parse_args():
                     help="experimental: replay the encoder fwd+bwd as CUDA graphs (capture currently fails with "
                          "cudaErrorStreamCaptureImplicit in the backward graph; see DESIGN.md)")
     ap.add_argument("--cpu-points", type=int, default=POINTS_PER_SCENE)
+    ap.add_argument("--profile-step", action="store_true",
+                    help="for `ncu --profile-from-start off`: after the warm-up run ONE step between "
+                         "cudaProfilerStart/Stop and exit (no timing, no JSON line)")
     return ap.parse_args()
 
 
@@ -193,6 +196,13 @@ def run_efgb200(args):
         if i == 0 and args.graph:
             model.capture_encoder_graph(args.scenes)  # encoder fwd+bwd as CUDA graph replays (static BEV shapes)
     barrier()
+
+    if args.profile_step:
+        torch.cuda.profiler.start()
+        step(resident[0])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
 
     launches0 = _lib.lib().efgb_launch_count()
     sampler = ClockSampler(local_rank)

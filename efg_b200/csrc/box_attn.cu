@@ -8,6 +8,8 @@
 // channels, so each bilinear corner is one coalesced 128-byte line, loc/attn are loaded once per
 // warp (lane p holds point p) and broadcast by shuffle, grad_loc/grad_attn are reduced with
 // shuffles, and grad_value is accumulated with one coalesced RED per corner.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace efgb {
@@ -228,6 +230,277 @@ box_attn_bwd_kernel(const float* __restrict__ value, const int64_t* __restrict__
   }
 }
 
+// =================================================================================================
+// head_dim == 32 specialisation ("tile" kernels) — the Voxel-DETR / ConQueR geometry (8 heads x 32 channels).
+//
+// The generic kernels above are issue-bound (every lane recomputes every tap's corner arithmetic) and, in the
+// encoder, L2-gather-bound (the 8 warps of a CTA are the 8 heads of ONE query, so nothing is shared in L1).
+// Here:
+//   * a CTA owns one head of an 8 x RY tile of queries (warp = query column, RY rows visited in turn).  When the
+//     caller says that consecutive queries form a row-major grid of width `qw` (encoder self-attention: the
+//     queries ARE the BEV cells) the tile is a 2-D patch whose sampling footprints overlap almost entirely, so
+//     the bilinear corner lines are served by L1 instead of L2.  `qw` is a locality hint only: every query is
+//     visited exactly once for any value of it.
+//   * lane p computes the corner arithmetic of tap p ONCE and parks (offset, attn * bilinear weight) for its four
+//     corners in shared memory;
+//   * in the tap loop the warp is split into 4 corner groups of 8 lanes, each lane owning 4 channels: ONE
+//     LDG.128 per tap fetches the four 128-byte corner lines, and (backward) ONE RED.128 per tap accumulates
+//     grad_value;
+//   * backward: the per-tap dot products <value_corner, grad_out> are reduced inside each 8-lane group with a
+//     transposing butterfly (7 shuffles per 8 taps) and handed back to the tap's owner lane through shared
+//     memory, which forms grad_attn and grad_loc from the four corner dots.
+// =================================================================================================
+constexpr int kTileWarps = 8;
+
+struct TileGeom {
+  int qw, qh;   // query grid (qw = 8, qh = ceil(LQ / 8) when no grid hint was given)
+  int tx, ty;   // tiles along x / y
+  int ry;       // query rows per tile
+};
+
+__device__ __forceinline__ void tile_fill_taps(int2* my, const int lane, const bool active, const float2 xy, const float a,
+                                               const int Hl, const int Wl, const int pix_stride, Corner* c, bool* made) {
+  int o1 = -1, o2 = -1, o3 = -1, o4 = -1;
+  c->w1 = c->w2 = c->w3 = c->w4 = 0.f;
+  c->lh = c->lw = c->hh = c->hw = 0.f;
+  *made = false;
+  if (active) {
+    float h_im, w_im;
+    if (make_corner(xy.x, xy.y, Hl, Wl, c, &h_im, &w_im)) {
+      *made = true;
+      const int base = (c->h_low * Wl + c->w_low) * pix_stride;
+      if (c->ok1) o1 = base;
+      if (c->ok2) o2 = base + pix_stride;
+      if (c->ok3) o3 = base + Wl * pix_stride;
+      if (c->ok4) o4 = base + (Wl + 1) * pix_stride;
+    }
+    int4* dst = reinterpret_cast<int4*>(my + lane * 4);
+    dst[0] = make_int4(o1, __float_as_int(c->w1 * a), o2, __float_as_int(c->w2 * a));
+    dst[1] = make_int4(o3, __float_as_int(c->w3 * a), o4, __float_as_int(c->w4 * a));
+  }
+}
+
+__global__ void __launch_bounds__(kTileWarps * 32)
+box_attn_fwd_tile_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
+                         const int64_t* __restrict__ level_start, const float* __restrict__ loc,
+                         const float* __restrict__ attn, const TileGeom g, int len_value, int num_heads, int num_levels,
+                         int len_query, int num_points, float* __restrict__ out) {
+  __shared__ int2 taps[kTileWarps][32 * 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cg = lane >> 3;        // corner group
+  const int cq = (lane & 7) * 4;   // first of this lane's 4 channels
+  int64_t blk = blockIdx.x;
+  const int tx = static_cast<int>(blk % g.tx);
+  blk /= g.tx;
+  const int ty = static_cast<int>(blk % g.ty);
+  blk /= g.ty;
+  const int h = static_cast<int>(blk % num_heads);
+  const int64_t b = blk / num_heads;
+  const int x = tx * kTileWarps + warp;
+  if (x >= g.qw) return;  // no block-wide barrier below
+  const int pix_stride = num_heads * 32;
+  int2* my = taps[warp];
+
+  for (int r = 0; r < g.ry; ++r) {
+    const int y = ty * g.ry + r;
+    const int64_t q = static_cast<int64_t>(y) * g.qw + x;
+    if (y >= g.qh || q >= len_query) break;
+    const int64_t idx = (b * len_query + q) * num_heads + h;
+    const float* loc_q = loc + idx * num_levels * num_points * 2;
+    const float* attn_q = attn + idx * num_levels * num_points;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int l = 0; l < num_levels; ++l) {
+      const int Hl = static_cast<int>(shapes[2 * l]), Wl = static_cast<int>(shapes[2 * l + 1]);
+      const float* vbase = value + (b * len_value + level_start[l]) * pix_stride + h * 32 + cq;
+      for (int p0 = 0; p0 < num_points; p0 += 32) {
+        const int p = p0 + lane;
+        const int np = min(32, num_points - p0);
+        float2 xy = make_float2(0.f, 0.f);
+        float a = 0.f;
+        if (p < num_points) {
+          xy = __ldg(reinterpret_cast<const float2*>(loc_q + (l * num_points + p) * 2));
+          a = __ldg(attn_q + l * num_points + p);
+        }
+        Corner c;
+        bool made;
+        __syncwarp();  // readers of the previous chunk are done with `my`
+        tile_fill_taps(my, lane, p < num_points, xy, a, Hl, Wl, pix_stride, &c, &made);
+        __syncwarp();
+        for (int t0 = 0; t0 < np; t0 += 5) {  // 5 independent corner-line loads in flight per lane (P = 25 = 5 x 5)
+          int2 e[5];
+          float4 v[5];
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            e[j] = make_int2(-1, 0);
+            if (t0 + j < np) e[j] = my[(t0 + j) * 4 + cg];  // warp-uniform guard
+          }
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e[j].x >= 0) v[j] = __ldg(reinterpret_cast<const float4*>(vbase + e[j].x));
+          }
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            const float w = e[j].x >= 0 ? __int_as_float(e[j].y) : 0.f;
+            acc.x = fmaf(w, v[j].x, acc.x);
+            acc.y = fmaf(w, v[j].y, acc.y);
+            acc.z = fmaf(w, v[j].z, acc.z);
+            acc.w = fmaf(w, v[j].w, acc.w);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 8; d <= 16; d <<= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, d);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, d);
+      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, d);
+      acc.w += __shfl_xor_sync(0xffffffffu, acc.w, d);
+    }
+    if (lane < 8) *reinterpret_cast<float4*>(out + idx * 32 + cq) = acc;
+  }
+}
+
+__global__ void __launch_bounds__(kTileWarps * 32)
+box_attn_bwd_tile_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
+                         const int64_t* __restrict__ level_start, const float* __restrict__ loc,
+                         const float* __restrict__ attn, const float* __restrict__ grad_out, const TileGeom g,
+                         int len_value, int num_heads, int num_levels, int len_query, int num_points,
+                         float* __restrict__ grad_value, float* __restrict__ grad_loc, float* __restrict__ grad_attn) {
+  __shared__ int2 taps[kTileWarps][32 * 4];
+  __shared__ __align__(16) float dots[kTileWarps][32 * 4];  // [tap][corner] = <value_corner, grad_out>
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cg = lane >> 3;
+  const int cq = (lane & 7) * 4;
+  int64_t blk = blockIdx.x;
+  const int tx = static_cast<int>(blk % g.tx);
+  blk /= g.tx;
+  const int ty = static_cast<int>(blk % g.ty);
+  blk /= g.ty;
+  const int h = static_cast<int>(blk % num_heads);
+  const int64_t b = blk / num_heads;
+  const int x = tx * kTileWarps + warp;
+  if (x >= g.qw) return;
+  const int pix_stride = num_heads * 32;
+  int2* my = taps[warp];
+  float* mydots = dots[warp];
+  const bool b2 = (lane & 4) != 0, b1 = (lane & 2) != 0, b0 = (lane & 1) != 0;
+
+  for (int r = 0; r < g.ry; ++r) {
+    const int y = ty * g.ry + r;
+    const int64_t q = static_cast<int64_t>(y) * g.qw + x;
+    if (y >= g.qh || q >= len_query) break;
+    const int64_t idx = (b * len_query + q) * num_heads + h;
+    const int64_t lp = static_cast<int64_t>(num_levels) * num_points;
+    const float* loc_q = loc + idx * lp * 2;
+    const float* attn_q = attn + idx * lp;
+    const float4 tg = __ldg(reinterpret_cast<const float4*>(grad_out + idx * 32 + cq));
+    for (int l = 0; l < num_levels; ++l) {
+      const int Hl = static_cast<int>(shapes[2 * l]), Wl = static_cast<int>(shapes[2 * l + 1]);
+      const int64_t voff = (b * len_value + level_start[l]) * pix_stride + h * 32 + cq;
+      const float* vbase = value + voff;
+      float* gbase = grad_value + voff;
+      for (int p0 = 0; p0 < num_points; p0 += 32) {
+        const int p = p0 + lane;
+        const int np = min(32, num_points - p0);
+        float2 xy = make_float2(0.f, 0.f);
+        float a = 0.f;
+        if (p < num_points) {
+          xy = __ldg(reinterpret_cast<const float2*>(loc_q + (l * num_points + p) * 2));
+          a = __ldg(attn_q + l * num_points + p);
+        }
+        Corner c;
+        bool made;
+        __syncwarp();  // owners of the previous chunk have read `mydots`, readers are done with `my`
+        tile_fill_taps(my, lane, p < num_points, xy, a, Hl, Wl, pix_stride, &c, &made);
+        __syncwarp();
+        for (int t0 = 0; t0 < np; t0 += 8) {
+          float d[8];
+#pragma unroll
+          for (int j0 = 0; j0 < 8; j0 += 4) {  // 4 independent corner-line loads in flight per lane
+            int2 e[4];
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              e[j] = make_int2(-1, 0);
+              if (t0 + j0 + j < np) e[j] = my[(t0 + j0 + j) * 4 + cg];  // warp-uniform guard
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (e[j].x >= 0) v[j] = __ldg(reinterpret_cast<const float4*>(vbase + e[j].x));
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              d[j0 + j] = v[j].x * tg.x + v[j].y * tg.y + v[j].z * tg.z + v[j].w * tg.w;
+              if (e[j].x >= 0) {
+                const float w = __int_as_float(e[j].y);
+                atomicAdd(reinterpret_cast<float4*>(gbase + e[j].x), make_float4(w * tg.x, w * tg.y, w * tg.z, w * tg.w));
+              }
+            }
+          }
+          // transposing butterfly over the 8 lanes of the corner group: lane j ends with the sum of d[j]
+          float e4[4], f2[2];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float send = b2 ? d[i] : d[i + 4];
+            const float keep = b2 ? d[i + 4] : d[i];
+            e4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const float send = b1 ? e4[i] : e4[i + 2];
+            const float keep = b1 ? e4[i + 2] : e4[i];
+            f2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+          }
+          const float send = b0 ? f2[0] : f2[1];
+          const float keep = b0 ? f2[1] : f2[0];
+          const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+          mydots[(t0 + (lane & 7)) * 4 + cg] = tot;
+        }
+        __syncwarp();
+        if (p < num_points) {
+          float gx = 0.f, gy = 0.f, ga = 0.f;
+          if (made) {
+            const float4 D = *reinterpret_cast<const float4*>(mydots + lane * 4);
+            ga = c.w1 * D.x + c.w2 * D.y + c.w3 * D.z + c.w4 * D.w;
+            const float gw = c.hh * (D.y - D.x) + c.lh * (D.w - D.z);
+            const float gh = c.hw * (D.z - D.x) + c.lw * (D.w - D.y);
+            gx = static_cast<float>(Wl) * gw * a;
+            gy = static_cast<float>(Hl) * gh * a;
+          }
+          *reinterpret_cast<float2*>(grad_loc + (idx * lp + l * num_points + p) * 2) = make_float2(gx, gy);
+          grad_attn[idx * lp + l * num_points + p] = ga;
+        }
+      }
+    }
+  }
+}
+
+// Tile geometry for `nw` = batch * len_query * num_heads warps of work.
+static TileGeom tile_geom(int len_query, int query_grid_w, int64_t nw) {
+  TileGeom g;
+  if (query_grid_w > 0 && query_grid_w <= len_query) {
+    g.qw = query_grid_w;
+  } else {
+    g.qw = kTileWarps;
+  }
+  g.qh = (len_query + g.qw - 1) / g.qw;
+  // tall tiles only while at least ~6 CTAs per SM remain
+  const int64_t rows = nw / (static_cast<int64_t>(kTileWarps) * kNumSMs * 6);
+  g.ry = rows >= 8 ? 8 : rows >= 4 ? 4 : rows >= 2 ? 2 : 1;
+  g.tx = (g.qw + kTileWarps - 1) / kTileWarps;
+  g.ty = (g.qh + g.ry - 1) / g.ry;
+  return g;
+}
+
+static bool use_tile_kernels(int len_value, int num_heads, int head_dim) {
+  if (head_dim != 32) return false;
+  if (static_cast<int64_t>(len_value) * num_heads * 32 >= (1ll << 31)) return false;  // 32-bit tap offsets
+  const char* e = getenv("EFGB_BOX_ATTN");
+  return !(e && strcmp(e, "generic") == 0);
+}
+
 static int check_args(int batch, int len_value, int num_heads, int head_dim, int num_levels, int len_query,
                       int num_points, const char* who) {
   EFGB_REQUIRE(batch >= 0 && len_value >= 0 && num_heads >= 1 && head_dim >= 1 && num_levels >= 1 && len_query >= 0 &&
@@ -243,14 +516,23 @@ using namespace efgb;
 
 extern "C" int efgb_box_attn_forward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start,
                                      const float* loc, const float* attn, int batch, int len_value, int num_heads,
-                                     int head_dim, int num_levels, int len_query, int num_points, float* out,
-                                     efgb_stream_t stream_) {
+                                     int head_dim, int num_levels, int len_query, int num_points, int query_grid_w,
+                                     float* out, efgb_stream_t stream_) {
   cudaStream_t stream = as_stream(stream_);
   int rc = check_args(batch, len_value, num_heads, head_dim, num_levels, len_query, num_points, "box_attn_forward");
   if (rc != EFGB_OK) return rc;
   const int64_t nw = static_cast<int64_t>(batch) * len_query * num_heads;
   if (nw == 0) return EFGB_OK;
   EFGB_REQUIRE(value && spatial_shapes && level_start && loc && attn && out, EFGB_EINVAL, "box_attn_forward: null pointer");
+  if (use_tile_kernels(len_value, num_heads, head_dim)) {
+    const TileGeom g = tile_geom(len_query, query_grid_w, nw);
+    const int64_t blocks = static_cast<int64_t>(batch) * num_heads * g.tx * g.ty;
+    EFGB_REQUIRE(blocks < (1ll << 31), EFGB_EINVAL, "box_attn_forward: too many query tiles");
+    box_attn_fwd_tile_kernel<<<static_cast<unsigned>(blocks), kTileWarps * 32, 0, stream>>>(
+        value, spatial_shapes, level_start, loc, attn, g, len_value, num_heads, num_levels, len_query, num_points, out);
+    EFGB_LAUNCH_OK("box_attn_fwd_tile_kernel");
+    return EFGB_OK;
+  }
   const unsigned nb = static_cast<unsigned>((nw + 7) / 8);
   const int nc = (head_dim + 31) / 32;
 #define EFGB_FWD(NC)                                                                                              \
@@ -267,8 +549,8 @@ extern "C" int efgb_box_attn_forward(const float* value, const int64_t* spatial_
 extern "C" int efgb_box_attn_backward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start,
                                       const float* loc, const float* attn, const float* grad_out, int batch,
                                       int len_value, int num_heads, int head_dim, int num_levels, int len_query,
-                                      int num_points, float* grad_value, float* grad_loc, float* grad_attn,
-                                      efgb_stream_t stream_) {
+                                      int num_points, int query_grid_w, float* grad_value, float* grad_loc,
+                                      float* grad_attn, efgb_stream_t stream_) {
   cudaStream_t stream = as_stream(stream_);
   int rc = check_args(batch, len_value, num_heads, head_dim, num_levels, len_query, num_points, "box_attn_backward");
   if (rc != EFGB_OK) return rc;
@@ -281,6 +563,16 @@ extern "C" int efgb_box_attn_backward(const float* value, const int64_t* spatial
   if (nw == 0) return EFGB_OK;
   EFGB_REQUIRE(value && spatial_shapes && level_start && loc && attn && grad_out && grad_loc && grad_attn, EFGB_EINVAL,
                "box_attn_backward: null pointer");
+  if (use_tile_kernels(len_value, num_heads, head_dim)) {
+    const TileGeom g = tile_geom(len_query, query_grid_w, nw);
+    const int64_t blocks = static_cast<int64_t>(batch) * num_heads * g.tx * g.ty;
+    EFGB_REQUIRE(blocks < (1ll << 31), EFGB_EINVAL, "box_attn_backward: too many query tiles");
+    box_attn_bwd_tile_kernel<<<static_cast<unsigned>(blocks), kTileWarps * 32, 0, stream>>>(
+        value, spatial_shapes, level_start, loc, attn, grad_out, g, len_value, num_heads, num_levels, len_query,
+        num_points, grad_value, grad_loc, grad_attn);
+    EFGB_LAUNCH_OK("box_attn_bwd_tile_kernel");
+    return EFGB_OK;
+  }
   const unsigned nb = static_cast<unsigned>((nw + 7) / 8);
   const int nc = (head_dim + 31) / 32;
 #define EFGB_BWD(NC)                                                                                               \

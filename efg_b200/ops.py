@@ -8,6 +8,7 @@ enqueues the CUDA kernels on the current stream.  There is no CPU path: CPU tens
 "Not implemented on the CPU" (voxelization.h:63, box_attn.h:53).
 """
 import ctypes
+import weakref
 
 import torch
 
@@ -446,13 +447,35 @@ def _box_attn_shapes(value, shapes, level_start, loc, attn):
     return b, lv, h, ch, nl, lq, npnt
 
 
+_shape_mirrors = {}
+
+
+def _query_grid_width(shapes, num_levels, len_query):
+    """Locality hint for the box-attention kernels: the width of the query grid when the queries are the
+    cells of a single-level value map (encoder self-attention), else 0.  `shapes` lives on the device; its host
+    mirror is fetched once per tensor (one D2H the first time a given shapes tensor is seen — the models keep
+    one per BEV geometry) and revalidated through the tensor's version counter.  The hint never changes results."""
+    if num_levels != 1:
+        return 0
+    key = (shapes.data_ptr(), shapes.numel())
+    ent = _shape_mirrors.get(key)
+    if ent is None or ent[0]() is None or ent[1] != shapes._version:
+        if len(_shape_mirrors) > 64:
+            _shape_mirrors.clear()
+        ent = (weakref.ref(shapes), shapes._version, shapes.tolist())
+        _shape_mirrors[key] = ent
+    hl, wl = ent[2][0]
+    return int(wl) if int(hl) * int(wl) == len_query else 0
+
+
 def box_attn_forward(value, shapes, level_start, loc, attn):
     b, lv, h, ch, nl, lq, npnt = _box_attn_shapes(value, shapes, level_start, loc, attn)
+    grid_w = _query_grid_width(shapes, nl, lq)
     out = torch.empty((b, lq, h * ch), dtype=torch.float32, device=value.device)
     L = _lib.lib()
     t0 = PROFILER.begin() if PROFILER is not None else None
     rc = L.efgb_box_attn_forward(_p(value), _p(shapes), _p(level_start), _p(loc), _p(attn), b, lv, h, ch, nl, lq, npnt,
-                                 _p(out), _stream())
+                                 grid_w, _p(out), _stream())
     _lib.check(rc, "box_attn_forward")
     if t0 is not None:
         nbytes = 4 * (value.numel() + loc.numel() + attn.numel() + out.numel())
@@ -463,13 +486,14 @@ def box_attn_forward(value, shapes, level_start, loc, attn):
 def box_attn_backward(value, shapes, level_start, loc, attn, grad_out):
     b, lv, h, ch, nl, lq, npnt = _box_attn_shapes(value, shapes, level_start, loc, attn)
     _check(grad_out, "grad_output", torch.float32)
+    grid_w = _query_grid_width(shapes, nl, lq)
     grad_value = torch.empty_like(value)
     grad_loc = torch.empty_like(loc)
     grad_attn = torch.empty_like(attn)
     L = _lib.lib()
     t0 = PROFILER.begin() if PROFILER is not None else None
     rc = L.efgb_box_attn_backward(_p(value), _p(shapes), _p(level_start), _p(loc), _p(attn), _p(grad_out), b, lv, h, ch,
-                                  nl, lq, npnt, _p(grad_value), _p(grad_loc), _p(grad_attn), _stream())
+                                  nl, lq, npnt, grid_w, _p(grad_value), _p(grad_loc), _p(grad_attn), _stream())
     _lib.check(rc, "box_attn_backward")
     if t0 is not None:
         nbytes = 4 * (2 * value.numel() + 2 * loc.numel() + 2 * attn.numel() + grad_out.numel())

@@ -199,17 +199,21 @@ int efgb_dense_to_sparse(const float* dense, const int32_t* coords, int64_t num_
  *   loc [B, LQ, H, L, P, 2] f32 (x,y in [0,1]); attn [B, LQ, H, L, P] f32; out [B, LQ, H*Ch].
  * backward zero-fills grad_value then accumulates with red.global.add; grad_loc / grad_attn
  * are written once per element (no atomics).
+ * query_grid_w is a LOCALITY HINT with no effect on the result: > 0 says that consecutive queries
+ * form a row-major grid of that width (encoder self-attention, where the queries are the BEV cells),
+ * so the kernel can give one CTA a 2-D patch of queries whose sampling footprints overlap; 0 = unknown.
  * ------------------------------------------------------------------------------------------ */
 int efgb_box_attn_forward(const float* value, const int64_t* spatial_shapes,
                           const int64_t* level_start, const float* loc, const float* attn,
                           int batch, int len_value, int num_heads, int head_dim, int num_levels,
-                          int len_query, int num_points, float* out, efgb_stream_t stream);
+                          int len_query, int num_points, int query_grid_w, float* out,
+                          efgb_stream_t stream);
 
 int efgb_box_attn_backward(const float* value, const int64_t* spatial_shapes,
                            const int64_t* level_start, const float* loc, const float* attn,
                            const float* grad_out, int batch, int len_value, int num_heads,
                            int head_dim, int num_levels, int len_query, int num_points,
-                           float* grad_value, float* grad_loc, float* grad_attn,
+                           int query_grid_w, float* grad_value, float* grad_loc, float* grad_attn,
                            efgb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
