@@ -43,13 +43,13 @@ def _digest(path, deps):
     return h.hexdigest()
 
 
-def _compile_one(nvcc, src, deps, verbose):
-    obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+def _compile_one(nvcc, src, deps, verbose, defines=(), tag=""):
+    obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + tag + ".o")
     stamp = obj + ".sha1"
-    dig = _digest(src, deps)
+    dig = _digest(src, deps) + "".join(defines)
     if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dig:
         return obj, ""
-    cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+    cmd = [nvcc] + NVCC_FLAGS + list(defines) + ["-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
@@ -60,8 +60,19 @@ def _compile_one(nvcc, src, deps, verbose):
     return obj, r.stderr if verbose else ""
 
 
-def build(verbose=False, force=False):
-    """Compile every .cu under csrc/ and link libefgb200.so. Returns the library path."""
+# Build variants for A/B measurements on the GPU box: name -> extra nvcc defines.  The default library is the
+# product; a variant is only loaded when EFGB_LIB_VARIANT names it (efg_b200/_lib.py).
+VARIANTS = {
+    "pw8": ["-DEFGB_TC_PRODUCER_WARPS=8"],
+    "pw16": ["-DEFGB_TC_PRODUCER_WARPS=16"],
+}
+
+
+def build(verbose=False, force=False, variant=None):
+    """Compile every .cu under csrc/ and link libefgb200.so (or libefgb200_<variant>.so). Returns the library path."""
+    defines = tuple(VARIANTS[variant]) if variant else ()
+    tag = "_" + variant if variant else ""
+    lib_path = LIB_PATH[:-3] + tag + ".so"
     nvcc = _nvcc()
     os.makedirs(OBJ_DIR, exist_ok=True)
     if force:
@@ -73,24 +84,25 @@ def build(verbose=False, force=False):
     )
     srcs = sources()
     with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        results = list(ex.map(lambda s: _compile_one(nvcc, s, deps, verbose), srcs))
+        results = list(ex.map(lambda s: _compile_one(nvcc, s, deps, verbose, defines, tag), srcs))
     objs = [o for o, _ in results]
     if verbose:
         for _, log in results:
             if log:
                 sys.stderr.write(log)
     newest = max(os.path.getmtime(o) for o in objs)
-    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < newest:
+    if force or not os.path.exists(lib_path) or os.path.getmtime(lib_path) < newest:
         # shared cudart: the library must use the SAME runtime instance as PyTorch (already loaded in the process)
         # so that stream capture (CUDA graphs) sees one consistent runtime; rpath is the fallback when torch is
         # not imported first
-        cmd = [nvcc, "-shared", "-cudart", "shared", "-o", LIB_PATH] + objs + [
+        cmd = [nvcc, "-shared", "-cudart", "shared", "-o", lib_path] + objs + [
             "-gencode", "arch=compute_100a,code=sm_100a", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))
+    var = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")]
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv, variant=var[0] if var else None))

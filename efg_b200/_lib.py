@@ -8,7 +8,9 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libefgb200.so")
+# EFGB_LIB_VARIANT=<name> loads libefgb200_<name>.so (an A/B build of the same sources, see _build.VARIANTS)
+_VARIANT = os.environ.get("EFGB_LIB_VARIANT", "")
+LIB_PATH = os.path.join(_HERE, "libefgb200%s.so" % ("_" + _VARIANT if _VARIANT else ""))
 
 _vp = ctypes.c_void_p
 _i64 = ctypes.c_int64
@@ -46,9 +48,12 @@ SIGNATURES = {
     "efgb_spconv_wgrad": (_int, [_vp, _i64, _int, _vp, _vp, _i64, _int, _int, _vp, _vp]),
     "efgb_sparse_to_dense": (_int, [_vp, _vp, _i64, _int, _int, _host_i32x3, _vp, _vp]),
     "efgb_dense_to_sparse": (_int, [_vp, _vp, _i64, _int, _int, _host_i32x3, _vp, _vp]),
+    "efgb_colsum_workspace_bytes": (_sz, [_i64, _int]),
+    "efgb_colsum": (_int, [_vp, _i64, _int, _vp, _vp, _sz, _vp]),
     "efgb_box_attn_forward": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _int, _vp, _vp]),
-    "efgb_box_grid_softmax_forward": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _vp, _vp, _vp]),
-    "efgb_box_grid_softmax_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _vp, _vp, _vp]),
+    "efgb_box_grid_softmax_forward": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _i64, _i64, _vp, _vp, _vp]),
+    "efgb_box_grid_softmax_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _i64, _i64, _vp, _vp,
+                                             _vp]),
     "efgb_box_attn_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _int,
                                       _vp, _vp, _vp, _vp]),
 }

@@ -609,16 +609,20 @@ template <bool kBackward>
 __global__ void __launch_bounds__(256)
 box_grid_softmax_kernel(const float* __restrict__ offsets, const float* __restrict__ logits, const float* __restrict__ ref,
                         const float* __restrict__ kidx, int64_t num_warps, int num_heads, int num_levels, int num_points,
-                        int nv, float* __restrict__ loc, float* __restrict__ attn, const float* __restrict__ g_loc,
+                        int nv, int64_t ld_logits, int64_t ld_offsets, float* __restrict__ loc, float* __restrict__ attn,
+                        const float* __restrict__ g_loc,
                         const float* __restrict__ g_attn, float* __restrict__ g_offsets, float* __restrict__ g_logits) {
   const int lane = threadIdx.x & 31;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (idx >= num_warps) return;
   const int64_t bq = idx / num_heads;
+  const int hd = static_cast<int>(idx - bq * num_heads);
   const float* r = ref + bq * 7;
   const float cx = r[0], cy = r[1], w = r[3], l = r[4], ref_angle = r[6];
   const int lp = num_levels * num_points;
-  const float* lg = logits + idx * lp;
+  // logits / offsets rows may be slices of a wider projection output (row strides ld_logits / ld_offsets)
+  const float* lg = logits + bq * ld_logits + static_cast<int64_t>(hd) * lp;
+  float* glg = kBackward ? g_logits + bq * ld_logits + static_cast<int64_t>(hd) * lp : nullptr;
 
   // ---- softmax over L*P logits (each lane strides over them)
   float m = -INFINITY;
@@ -637,13 +641,14 @@ box_grid_softmax_kernel(const float* __restrict__ offsets, const float* __restri
     dot = warp_sum(dot);
     for (int e = lane; e < lp; e += 32) {
       const float a = expf(lg[e] - m) * inv;
-      g_logits[idx * lp + e] = a * (g_attn[idx * lp + e] - dot);
+      glg[e] = a * (g_attn[idx * lp + e] - dot);
     }
   }
 
   // ---- sampling grid
   for (int lvl = 0; lvl < num_levels; ++lvl) {
-    const float* off = offsets + (idx * num_levels + lvl) * nv;
+    const int64_t off_at = bq * ld_offsets + (static_cast<int64_t>(hd) * num_levels + lvl) * nv;
+    const float* off = offsets + off_at;
     const float o0 = off[0], o1 = off[1], o2 = off[2], o3 = off[3];
     const float bx = cx + o0 / 8.f * w, by = cy + o1 / 8.f * l;
     const float sw = w + o2 / 8.f * w, sl = l + o3 / 8.f * l;
@@ -679,7 +684,7 @@ box_grid_softmax_kernel(const float* __restrict__ offsets, const float* __restri
       a_sl = warp_sum(a_sl);
       a_ang = warp_sum(a_ang);
       if (lane == 0) {
-        float* go = g_offsets + (idx * num_levels + lvl) * nv;
+        float* go = g_offsets + off_at;
         go[0] = a_cx * w / 8.f;
         go[1] = a_cy * l / 8.f;
         go[2] = (sw > 0.f ? a_sw : 0.f) * w / 8.f;
@@ -694,17 +699,19 @@ box_grid_softmax_kernel(const float* __restrict__ offsets, const float* __restri
 
 extern "C" int efgb_box_grid_softmax_forward(const float* offsets, const float* logits, const float* ref_windows,
                                              const float* kernel_indices, int64_t num_bq, int num_heads, int num_levels,
-                                             int num_points, int num_variables, float* loc, float* attn,
-                                             efgb_stream_t stream_) {
+                                             int num_points, int num_variables, int64_t logits_row_stride,
+                                             int64_t offsets_row_stride, float* loc, float* attn, efgb_stream_t stream_) {
   cudaStream_t stream = as_stream(stream_);
   EFGB_REQUIRE(num_bq >= 0 && num_heads >= 1 && num_levels >= 1 && num_points >= 1 && (num_variables == 4 || num_variables == 5),
                EFGB_EINVAL, "box_grid_softmax_forward: bad shape");
   const int64_t nw = num_bq * num_heads;
   if (nw == 0) return EFGB_OK;
   EFGB_REQUIRE(offsets && logits && ref_windows && kernel_indices && loc && attn, EFGB_EINVAL, "box_grid_softmax_forward: null pointer");
+  const int64_t ldl = logits_row_stride > 0 ? logits_row_stride : static_cast<int64_t>(num_heads) * num_levels * num_points;
+  const int64_t ldo = offsets_row_stride > 0 ? offsets_row_stride : static_cast<int64_t>(num_heads) * num_levels * num_variables;
   box_grid_softmax_kernel<false><<<static_cast<unsigned>((nw + 7) / 8), 256, 0, stream>>>(
-      offsets, logits, ref_windows, kernel_indices, nw, num_heads, num_levels, num_points, num_variables, loc, attn, nullptr,
-      nullptr, nullptr, nullptr);
+      offsets, logits, ref_windows, kernel_indices, nw, num_heads, num_levels, num_points, num_variables, ldl, ldo, loc, attn,
+      nullptr, nullptr, nullptr, nullptr);
   EFGB_LAUNCH_OK("box_grid_softmax_kernel<fwd>");
   return EFGB_OK;
 }
@@ -712,8 +719,8 @@ extern "C" int efgb_box_grid_softmax_forward(const float* offsets, const float* 
 extern "C" int efgb_box_grid_softmax_backward(const float* offsets, const float* logits, const float* ref_windows,
                                               const float* kernel_indices, const float* grad_loc, const float* grad_attn,
                                               int64_t num_bq, int num_heads, int num_levels, int num_points,
-                                              int num_variables, float* grad_offsets, float* grad_logits,
-                                              efgb_stream_t stream_) {
+                                              int num_variables, int64_t logits_row_stride, int64_t offsets_row_stride,
+                                              float* grad_offsets, float* grad_logits, efgb_stream_t stream_) {
   cudaStream_t stream = as_stream(stream_);
   EFGB_REQUIRE(num_bq >= 0 && num_heads >= 1 && num_levels >= 1 && num_points >= 1 && (num_variables == 4 || num_variables == 5),
                EFGB_EINVAL, "box_grid_softmax_backward: bad shape");
@@ -721,9 +728,11 @@ extern "C" int efgb_box_grid_softmax_backward(const float* offsets, const float*
   if (nw == 0) return EFGB_OK;
   EFGB_REQUIRE(offsets && logits && ref_windows && kernel_indices && grad_loc && grad_attn && grad_offsets && grad_logits, EFGB_EINVAL,
                "box_grid_softmax_backward: null pointer");
+  const int64_t ldl = logits_row_stride > 0 ? logits_row_stride : static_cast<int64_t>(num_heads) * num_levels * num_points;
+  const int64_t ldo = offsets_row_stride > 0 ? offsets_row_stride : static_cast<int64_t>(num_heads) * num_levels * num_variables;
   box_grid_softmax_kernel<true><<<static_cast<unsigned>((nw + 7) / 8), 256, 0, stream>>>(
-      offsets, logits, ref_windows, kernel_indices, nw, num_heads, num_levels, num_points, num_variables, nullptr, nullptr,
-      grad_loc, grad_attn, grad_offsets, grad_logits);
+      offsets, logits, ref_windows, kernel_indices, nw, num_heads, num_levels, num_points, num_variables, ldl, ldo, nullptr,
+      nullptr, grad_loc, grad_attn, grad_offsets, grad_logits);
   EFGB_LAUNCH_OK("box_grid_softmax_kernel<bwd>");
   return EFGB_OK;
 }

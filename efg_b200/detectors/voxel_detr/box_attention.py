@@ -87,18 +87,35 @@ class Box3dAttention(nn.Module):
         if v_mask is not None:
             value = value.masked_fill(v_mask[..., None], float(0))
         value = value.view(B, LV, self.num_head, self.head_dim)
-        attn = F.linear(query, self.linear_attn_weight, self.linear_attn_bias)
-        if (self._backend[0].name == "efgb200-cuda" and query.is_cuda and v_valid_ratios is None and
-                ref_windows.dim() == 3 and ref_windows.shape[-1] == 7):
-            # fused sampling grid + softmax (csrc/box_attn.cu), same math as the branch below
+        fused = (self._backend[0].name == "efgb200-cuda" and query.is_cuda and v_valid_ratios is None and
+                 ref_windows.dim() == 3 and ref_windows.shape[-1] == 7)
+        attn = None
+        if fused:
+            # fused sampling grid + softmax (csrc/box_attn.cu), same math as the torch chain in the else-branch
             from ... import ops
 
-            offsets = F.linear(query, self.linear_box_weight, self.linear_box_bias)
-            grid, attn = ops.BoxGridSoftmaxFunction.apply(
-                offsets.view(B, LQ, self.num_head, self.num_level, self.num_variable),
-                attn.view(B, LQ, self.num_head, -1), ref_windows, self.kernel_indices)
+            n_attn, n_box = self.linear_attn_weight.shape[0], self.linear_box_weight.shape[0]
+            ld = (n_attn + n_box + 63) // 64 * 64  # 256 for 8 heads x 25 taps (+ 4|5 box variables)
+            if ops.dense_linear_supported(B * LQ, self.d_model, ld):
+                # many rows (encoder): both projections as ONE tensor-core GEMM [attn logits | box offsets | 0-pad]
+                pad = ld - n_attn - n_box
+                ws = [self.linear_attn_weight, self.linear_box_weight]
+                bs = [self.linear_attn_bias, self.linear_box_bias]
+                if pad:
+                    ws.append(self.linear_attn_weight.new_zeros((pad, self.d_model)))
+                    bs.append(self.linear_attn_bias.new_zeros((pad,)))
+                proj = ops.dense_linear(query, torch.cat(ws, 0), torch.cat(bs, 0))
+                grid, attn = ops.BoxProjGridSoftmaxFunction.apply(proj, ref_windows, self.kernel_indices, self.num_head,
+                                                                  self.num_level, self.num_variable)
+            else:
+                attn = F.linear(query, self.linear_attn_weight, self.linear_attn_bias)
+                offsets = F.linear(query, self.linear_box_weight, self.linear_box_bias)
+                grid, attn = ops.BoxGridSoftmaxFunction.apply(
+                    offsets.view(B, LQ, self.num_head, self.num_level, self.num_variable),
+                    attn.view(B, LQ, self.num_head, -1), ref_windows, self.kernel_indices)
             attn = attn.view(B, LQ, self.num_head, self.num_level, self.kernel_size, self.kernel_size)
         else:
+            attn = F.linear(query, self.linear_attn_weight, self.linear_attn_bias)
             attn = F.softmax(attn.view(B, LQ, self.num_head, -1), dim=-1)
             attn = attn.view(B, LQ, self.num_head, self.num_level, self.kernel_size, self.kernel_size)
             grid = self._where_to_attend(query, v_valid_ratios, ref_windows)

@@ -342,6 +342,22 @@ def spconv_tc_wgrad(feats, grad_out, nbr, taps, c_in, c_out):
     return dw
 
 
+def colsum(x2d):
+    """x2d [rows, cols] f32 contiguous -> [cols] column sums (deterministic two-pass kernel)."""
+    _check(x2d, "x", torch.float32)
+    rows, cols = x2d.shape
+    if cols % 4 != 0:
+        raise RuntimeError("colsum: the number of columns must be a multiple of 4, got %d" % cols)
+    out = torch.empty((cols,), dtype=torch.float32, device=x2d.device)
+    L = _lib.lib()
+    ws = workspace(L.efgb_colsum_workspace_bytes(rows, cols), x2d.device)
+    t0 = PROFILER.begin() if PROFILER is not None else None
+    _lib.check(L.efgb_colsum(_p(x2d), rows, cols, _p(out), _p(ws), ws.numel(), _stream()), "colsum")
+    if t0 is not None:
+        PROFILER.end("colsum", t0, 4 * (x2d.numel() + cols))
+    return out
+
+
 class _DenseLinearFn(torch.autograd.Function):
     """y = x @ W^T + b on the tensor-core gather-GEMM kernels with an identity rulebook (a dense layer is a
     1-tap sparse conv over all rows).  fp32-faithful in "fp32x3" mode; used for the large token-wise linears
@@ -366,7 +382,7 @@ class _DenseLinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = spconv_tc_wgrad(x2d, grad_out, None, 1, c_in, c_out).view(c_out, c_in)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = grad_out.sum(0)
+            db = colsum(grad_out) if grad_out.shape[1] % 4 == 0 else grad_out.sum(0)
         return dx, dw, db
 
 
@@ -521,7 +537,7 @@ class BoxGridSoftmaxFunction(torch.autograd.Function):
         L = _lib.lib()
         t0 = PROFILER.begin() if PROFILER is not None else None
         _lib.check(L.efgb_box_grid_softmax_forward(_p(offsets), _p(logits), _p(ref_windows), _p(kernel_indices), b * lq, h, nl,
-                                                   npnt, nv, _p(loc), _p(attn), _stream()), "box_grid_softmax_forward")
+                                                   npnt, nv, 0, 0, _p(loc), _p(attn), _stream()), "box_grid_softmax_forward")
         if t0 is not None:
             PROFILER.end("box_grid_softmax_fwd", t0, 4 * (offsets.numel() + 2 * logits.numel() + loc.numel()))
         ctx.save_for_backward(offsets, logits, ref_windows, kernel_indices)
@@ -539,8 +555,63 @@ class BoxGridSoftmaxFunction(torch.autograd.Function):
         L = _lib.lib()
         t0 = PROFILER.begin() if PROFILER is not None else None
         _lib.check(L.efgb_box_grid_softmax_backward(_p(offsets), _p(logits), _p(ref_windows), _p(kernel_indices), _p(g_loc),
-                                                    _p(g_attn), b * lq, h, nl, npnt, nv, _p(g_off), _p(g_log), _stream()),
+                                                    _p(g_attn), b * lq, h, nl, npnt, nv, 0, 0, _p(g_off), _p(g_log), _stream()),
                    "box_grid_softmax_backward")
         if t0 is not None:
             PROFILER.end("box_grid_softmax_bwd", t0, 4 * (2 * offsets.numel() + 3 * logits.numel() + g_loc.numel()))
         return g_off, g_log, None, None
+
+
+class BoxProjGridSoftmaxFunction(torch.autograd.Function):
+    """Same op as BoxGridSoftmaxFunction, but logits and offsets are column slices of ONE projection output
+    proj [B, LQ, ld] = [attention logits (H*L*P) | box offsets (H*L*NV) | zero padding]: the two linear layers of
+    Box3dAttention (VD/modules/box_attention.py:66, :106) run as a single tensor-core GEMM, and the backward writes
+    both gradients straight into one [B, LQ, ld] buffer (no slicing / concatenation kernels)."""
+
+    @staticmethod
+    def forward(ctx, proj, ref_windows, kernel_indices, num_heads, num_levels, num_variables):
+        proj = proj.contiguous()
+        ref_windows, kernel_indices = ref_windows.contiguous(), kernel_indices.contiguous()
+        for t, n in ((proj, "proj"), (ref_windows, "ref_windows"), (kernel_indices, "kernel_indices")):
+            _check(t, n, torch.float32)
+        b, lq, ld = proj.shape
+        npnt = kernel_indices.shape[0]
+        n_attn = num_heads * num_levels * npnt
+        n_box = num_heads * num_levels * num_variables
+        if ld < n_attn + n_box or ref_windows.shape != (b, lq, 7):
+            raise RuntimeError("box_proj_grid_softmax: inconsistent shapes %r %r" % (tuple(proj.shape), tuple(ref_windows.shape)))
+        loc = torch.empty((b, lq, num_heads, num_levels, npnt, 2), dtype=torch.float32, device=proj.device)
+        attn = torch.empty((b, lq, num_heads, num_levels * npnt), dtype=torch.float32, device=proj.device)
+        L = _lib.lib()
+        off_ptr = ctypes.c_void_p(proj.data_ptr() + 4 * n_attn)
+        t0 = PROFILER.begin() if PROFILER is not None else None
+        _lib.check(L.efgb_box_grid_softmax_forward(off_ptr, _p(proj), _p(ref_windows), _p(kernel_indices), b * lq, num_heads,
+                                                   num_levels, npnt, num_variables, ld, ld, _p(loc), _p(attn), _stream()),
+                   "box_grid_softmax_forward")
+        if t0 is not None:
+            PROFILER.end("box_grid_softmax_fwd", t0, 4 * (b * lq * (n_attn + n_box) + attn.numel() + loc.numel()))
+        ctx.save_for_backward(proj, ref_windows, kernel_indices)
+        ctx.dims = (num_heads, num_levels, num_variables, n_attn, n_box)
+        return loc, attn
+
+    @staticmethod
+    def backward(ctx, g_loc, g_attn):
+        proj, ref_windows, kernel_indices = ctx.saved_tensors
+        num_heads, num_levels, num_variables, n_attn, n_box = ctx.dims
+        b, lq, ld = proj.shape
+        npnt = kernel_indices.shape[0]
+        g_loc = g_loc.contiguous() if g_loc is not None else torch.zeros((b, lq, num_heads, num_levels, npnt, 2), device=proj.device)
+        g_attn = g_attn.contiguous() if g_attn is not None else torch.zeros((b, lq, num_heads, num_levels * npnt), device=proj.device)
+        g_proj = torch.empty_like(proj)
+        if ld > n_attn + n_box:
+            g_proj[..., n_attn + n_box:].zero_()
+        L = _lib.lib()
+        off_ptr = ctypes.c_void_p(proj.data_ptr() + 4 * n_attn)
+        g_off_ptr = ctypes.c_void_p(g_proj.data_ptr() + 4 * n_attn)
+        t0 = PROFILER.begin() if PROFILER is not None else None
+        _lib.check(L.efgb_box_grid_softmax_backward(off_ptr, _p(proj), _p(ref_windows), _p(kernel_indices), _p(g_loc), _p(g_attn),
+                                                    b * lq, num_heads, num_levels, npnt, num_variables, ld, ld, g_off_ptr,
+                                                    _p(g_proj), _stream()), "box_grid_softmax_backward")
+        if t0 is not None:
+            PROFILER.end("box_grid_softmax_bwd", t0, 4 * (2 * b * lq * (n_attn + n_box) + g_attn.numel() + g_loc.numel()))
+        return g_proj, None, None, None, None, None

@@ -191,6 +191,16 @@ int efgb_dense_to_sparse(const float* dense, const int32_t* coords, int64_t num_
                          int batch, const int32_t* grid_dhw_host3, float* feats, efgb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Column sums out[c] = sum_r x[r, c] of a row-major [rows, cols] f32 matrix (cols % 4 == 0): the bias
+ * gradient of the token-wise linear layers (autograd of F.linear in VD/transformer.py:41-64 and
+ * VD/modules/box_attention.py:97-115, i.e. grad_out.sum(0) over B * 35 344 rows).  Deterministic
+ * (two passes, no atomics).  workspace: efgb_colsum_workspace_bytes(rows, cols).
+ * ------------------------------------------------------------------------------------------ */
+size_t efgb_colsum_workspace_bytes(int64_t rows, int cols);
+int efgb_colsum(const float* x, int64_t rows, int cols, float* out, void* workspace,
+                size_t workspace_bytes, efgb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Box attention (box_attn.h:29-83; kernels box_attn_kernel.cuh:275-351 fwd, :35-190 math):
  *   out[b,q,h,c] = sum_{l,p} attn[b,q,h,l,p] * bilinear(value_l[b,:,h,c], loc[b,q,h,l,p])
  * with h_im = loc_y*H_l - 0.5, w_im = loc_x*W_l - 0.5, zero padding, taps taken only when
@@ -223,16 +233,21 @@ int efgb_box_attn_backward(const float* value, const int64_t* spatial_shapes,
  * loc [BQ, H, L, P, 2] and the softmax weights attn [BQ, H, L*P] that efgb_box_attn_* consume.
  *   offsets [BQ, H, L, NV] (NV = 4, or 5 with rotation), logits [BQ, H, L*P], ref_windows [BQ, 7]
  *   (cx, cy, cz, w, l, h, angle; no gradient), kernel_indices [P, 2].
+ * logits / offsets (and their gradients) may be column slices of one wider projection output
+ * [BQ, ld]: logits_row_stride / offsets_row_stride give the floats between consecutive BQ rows
+ * (0 = densely packed, H*L*P and H*L*NV).
  * ------------------------------------------------------------------------------------------ */
 int efgb_box_grid_softmax_forward(const float* offsets, const float* logits, const float* ref_windows,
                                   const float* kernel_indices, int64_t num_bq, int num_heads,
-                                  int num_levels, int num_points, int num_variables, float* loc,
+                                  int num_levels, int num_points, int num_variables,
+                                  int64_t logits_row_stride, int64_t offsets_row_stride, float* loc,
                                   float* attn, efgb_stream_t stream);
 int efgb_box_grid_softmax_backward(const float* offsets, const float* logits, const float* ref_windows,
                                    const float* kernel_indices, const float* grad_loc,
                                    const float* grad_attn, int64_t num_bq, int num_heads, int num_levels,
-                                   int num_points, int num_variables, float* grad_offsets,
-                                   float* grad_logits, efgb_stream_t stream);
+                                   int num_points, int num_variables, int64_t logits_row_stride,
+                                   int64_t offsets_row_stride, float* grad_offsets, float* grad_logits,
+                                   efgb_stream_t stream);
 
 #ifdef __cplusplus
 }

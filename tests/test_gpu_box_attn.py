@@ -136,3 +136,53 @@ def test_fused_grid_softmax_matches_torch_chain(with_rotation):
     assert (grid2 - grid1).abs().max().item() < 1e-5
     assert (attn2 - attn1).abs().max().item() < 1e-6
     assert (q2.grad - q1.grad).abs().max().item() < 1e-4 * max(1.0, q1.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("with_rotation", [False, True])
+def test_box3d_attention_merged_projection_matches_torch_chain(with_rotation):
+    """Encoder-sized inputs take the merged path (both projections as ONE tensor-core GEMM feeding the strided
+    grid/softmax kernel); it must agree with the reference's chain of separate F.linear + torch ops on the same
+    parameters, forward and gradients."""
+    from efg_b200.detectors.voxel_detr.box_attention import Box3dAttention
+    from oracle.backend_cpu import cpu_backend
+
+    torch.manual_seed(5)
+    hh = ww = 72
+    B, LQ, d, H = 1, hh * ww, 256, 8  # 5184 rows >= the 4096-row threshold of the dense tensor-core path
+    ref_mod = Box3dAttention(d, 1, H, with_rotation=with_rotation, backend=cpu_backend()).cuda()
+    fast_mod = Box3dAttention(d, 1, H, with_rotation=with_rotation).cuda()
+    with torch.no_grad():
+        ref_mod.linear_box_weight.normal_(0, 0.05)
+        ref_mod.linear_attn_weight.normal_(0, 0.05)
+    fast_mod.load_state_dict(ref_mod.state_dict())
+    shapes = torch.tensor([[hh, ww]], dtype=torch.int64, device="cuda")
+    start = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ys, xs = torch.meshgrid(torch.linspace(0.5, hh - 0.5, hh, device="cuda") / hh,
+                            torch.linspace(0.5, ww - 0.5, ww, device="cuda") / ww, indexing="ij")
+    ref = torch.zeros(B, LQ, 7, device="cuda")
+    ref[..., 0], ref[..., 1] = xs.reshape(-1), ys.reshape(-1)
+    ref[..., 3:5] = 0.06
+    ref[..., 6] = 0.1
+    query = torch.randn(B, LQ, d, device="cuda")
+    value = torch.randn(B, LQ, d, device="cuda")
+    g = torch.randn(B, LQ, d, device="cuda")
+    outs = []
+    for mod in (ref_mod, fast_mod):
+        q = query.clone().requires_grad_(True)
+        v = value.clone().requires_grad_(True)
+        out, attn = mod(q, v, shapes, None, start, None, ref)
+        (out * g).sum().backward()
+        outs.append((out.detach(), attn.detach(), q.grad, v.grad, mod.linear_box_weight.grad, mod.linear_attn_weight.grad,
+                     mod.linear_box_bias.grad, mod.linear_attn_bias.grad))
+    names = ("out", "attn", "dquery", "dvalue", "dW_box", "dW_attn", "db_box", "db_attn")
+    for n, a, b in zip(names, *outs):
+        scale = max(1.0, a.abs().max().item())
+        diff = (a - b).abs()
+        if n == "dquery":
+            # d(bilinear sample)/d(location) is piecewise constant per BEV cell: a sampling location that lands within
+            # 1 ulp of a cell border may floor() to the other cell in one of the two implementations, which changes
+            # that query's gradient by O(1).  Allow a vanishing fraction of such rows, require the rest to agree.
+            bad_rows = (diff.amax(-1) > 2e-4 * scale).float().mean().item()
+            assert bad_rows < 2e-3, (n, bad_rows)
+        else:
+            assert diff.max().item() < 2e-4 * scale, (n, diff.max().item(), scale)
