@@ -73,6 +73,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// Ampere-style asynchronous 16-byte copy global -> shared; src_bytes = 0 writes zeros (missing neighbour).
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// The mbarrier receives one arrival from this thread once all of its earlier cp.async copies have landed
+// (.noinc: the arrival is part of the barrier's initial count).
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -130,7 +139,11 @@ struct Params {
   int tiles_per_super;   // T: row tiles that share every weight chunk (accumulators side by side in TMEM)
   int num_super;         // ceil(num_tiles / T)
   int sa, sb;            // A-ring / B-ring depth
-  int debug;             // perf experiments only: 1 = no MMAs, 2 = no gather loads, 4 = no index loads
+  int async_gather;      // 1: cp.async producers (produce_a_async), 0: register-staged producers (produce_a)
+  int cred_shift;        // log2(c_red) when c_red is a power of two, else -1
+  int debug;             // perf experiments only: 1 = no MMAs, 2 = no gather loads, 4 = no index loads,
+                         // 64 = async producers leave the raw fp32 words as the hi operand (relies on the tensor core
+                         // ignoring the 13 low mantissa bits)
 };
 
 template <bool kSplit>
@@ -262,6 +275,117 @@ __device__ __forceinline__ void produce_a(const Params& p, const CtaWork& w, uin
   }
 }
 
+// A producers, asynchronous variant.  All producer warps work on the SAME stage; a thread owns two 16-byte pieces
+// of the 128 x 128 B tile.  The gather itself is cp.async (LDGSTS): the row piece lands in its swizzled slot of the
+// stage without passing through registers, so `sa - 2` stages of gathers are in flight per CTA while the oldest
+// landed stage is split into tf32 hi / lo in place (LDS, 8 ALU ops, 2 STS per piece) — neither the rulebook
+// latency nor the gather latency sits on the critical path of a stage any more.
+//   a_empty[slot] (MMA commit)  ->  cp.async into slot, cp.async.mbarrier.arrive on raw_full[slot]
+//   raw_full[slot] (all copies landed)  ->  split in place, fence.proxy.async, a_full[slot]  ->  MMA
+template <bool kSplit>
+__device__ __forceinline__ void produce_a_async(const Params& p, const CtaWork& w, uint8_t* a_ring, uint64_t* a_full,
+                                                uint64_t* a_empty, uint64_t* raw_full, const int tid, const int lane) {
+  constexpr int kThreadsP = kProducerWarps * 32;
+  constexpr int kPieces = (kTileM * 8) / kThreadsP;    // 16-byte pieces per thread per stage
+  constexpr int kRowsPerPass = kThreadsP / 8;
+  const int a_part = kTileM * 128;
+  const int a_bytes = Smem<kSplit>::a_bytes();
+  const int q = tid & 7;            // 16-byte piece of the 128-byte row
+  const int r_base = tid >> 3;      // row of piece 0; piece i is row r_base + i * kRowsPerPass
+  uint32_t off[kPieces];
+#pragma unroll
+  for (int i = 0; i < kPieces; ++i) {
+    const int r = r_base + i * kRowsPerPass;
+    off[i] = static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(q ^ (r & 7)) << 4);
+  }
+  const int total = w.total_a;
+  if (total == 0) return;
+  const int depth = p.sa - 2;       // stages of gathers in flight ahead of the one being split (host ensures sa >= 3)
+
+  // cursor over this CTA's stage stream (super-tile, chunk, tile-in-super-tile), advanced without divisions
+  int ci_s = 0, cc = 0, ct = 0, cti = w.tiles_in(p, 0);
+  int32_t src[kPieces];
+  int ci = 0;
+  auto load_idx = [&]() {
+    const int tile = (static_cast<int>(blockIdx.x) + ci_s * static_cast<int>(gridDim.x)) * p.tiles_per_super + ct;
+    const int64_t r0 = static_cast<int64_t>(tile) * kTileM;
+    const int kk = cc * kChunkK + q * 4;
+    const int tap = p.cred_shift >= 0 ? (kk >> p.cred_shift) : kk / p.c_red;
+    ci = kk - tap * p.c_red;
+    const bool tap_ok = tap < p.taps;
+#pragma unroll
+    for (int i = 0; i < kPieces; ++i) {
+      const int64_t row = r0 + r_base + i * kRowsPerPass;
+      int32_t v = -1;
+      if (tap_ok && row < p.num_out) v = p.nbr ? __ldg(p.nbr + row * p.taps + tap) : static_cast<int32_t>(row);
+      src[i] = v;
+    }
+    if (++ct == cti) {  // advance the cursor
+      ct = 0;
+      if (++cc == p.chunks) {
+        cc = 0;
+        ++ci_s;
+        cti = w.tiles_in(p, ci_s);
+      }
+    }
+  };
+
+  int islot = 0;
+  uint32_t iphase = 0;
+  int issued = 0;
+  auto issue = [&]() {  // gather stage `issued` with the indices loaded by the previous call
+    mbar_wait(smem_u32(&a_empty[islot]), iphase ^ 1);
+    const uint32_t dst = smem_u32(a_ring + static_cast<size_t>(islot) * a_bytes);
+#pragma unroll
+    for (int i = 0; i < kPieces; ++i) {
+      const bool ok = src[i] >= 0;
+      const float* g = ok ? p.in + static_cast<int64_t>(src[i]) * p.c_red + ci : p.in;
+      cp_async_16(dst + off[i], g, ok ? 16u : 0u);
+    }
+    cp_async_mbar_arrive_noinc(smem_u32(&raw_full[islot]));
+    if (++islot == p.sa) {
+      islot = 0;
+      iphase ^= 1;
+    }
+    if (++issued < total) load_idx();  // consumed by the next issue(); its latency hides behind the split below
+  };
+
+  load_idx();
+  for (int t = 0; t < depth && t < total; ++t) issue();
+  int sslot = 0;
+  uint32_t sphase = 0;
+  for (int s = 0; s < total; ++s) {
+    if (issued < total) issue();
+    mbar_wait(smem_u32(&raw_full[sslot]), sphase);
+    uint8_t* a_hi = a_ring + static_cast<size_t>(sslot) * a_bytes;
+    uint8_t* a_lo = a_hi + a_part;
+    if (kSplit) {
+#pragma unroll
+      for (int i = 0; i < kPieces; ++i) {
+        const float4 v = *reinterpret_cast<const float4*>(a_hi + off[i]);
+        float4 hi, lo;
+        hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+        hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+        hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+        hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+        lo.x = v.x - hi.x;
+        lo.y = v.y - hi.y;
+        lo.z = v.z - hi.z;
+        lo.w = v.w - hi.w;
+        if (!(p.debug & 64)) *reinterpret_cast<float4*>(a_hi + off[i]) = hi;
+        *reinterpret_cast<float4*>(a_lo + off[i]) = lo;
+      }
+    }
+    fence_proxy_async();  // cp.async / st.shared writes -> visible to the tensor core (async proxy)
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&a_full[sslot]));
+    if (++sslot == p.sa) {
+      sslot = 0;
+      sphase ^= 1;
+    }
+  }
+}
+
 template <bool kSplit>
 __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -284,7 +408,8 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p) 
   uint64_t* b_empty = b_full + p.sb;
   uint64_t* tmem_full = b_empty + p.sb;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* raw_full = tmem_empty + 2;   // [sa], async producers only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_full + p.sa);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -296,8 +421,9 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p) 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.sa; ++s) {
-      mbar_init(smem_u32(&a_full[s]), kProducerWarps / groups);
+      mbar_init(smem_u32(&a_full[s]), p.async_gather ? kProducerWarps : kProducerWarps / groups);
       mbar_init(smem_u32(&a_empty[s]), 1);
+      mbar_init(smem_u32(&raw_full[s]), kProducerWarps * 32);
     }
     for (int s = 0; s < p.sb; ++s) {
       mbar_init(smem_u32(&b_full[s]), 1);
@@ -322,7 +448,9 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p) 
 
   if (warp < kProducerWarps) {
     // ================= A producers =================
-    if (groups == 4)
+    if (p.async_gather)
+      produce_a_async<kSplit>(p, w, a_ring, a_full, a_empty, raw_full, static_cast<int>(threadIdx.x), lane);
+    else if (groups == 4)
       produce_a<kSplit, 4>(p, w, a_ring, a_full, a_empty, warp, lane);
     else
       produce_a<kSplit, 2>(p, w, a_ring, a_full, a_empty, warp, lane);
@@ -557,6 +685,10 @@ __device__ __forceinline__ void split_store(uint8_t* hi_base, uint8_t* lo_base, 
 
 // wgrad producers: kGroups warp groups, group g owns every kGroups-th 32-row stage of this CTA's stage
 // stream (every work item has exactly rows_per_chunk/32 stage slots; slots past the end are zero tiles).
+// All per-piece index arithmetic is hoisted: a thread's A pieces share one 16-byte column (tap and channel change
+// only with the work item) and walk the rows with a constant stride, likewise its grad_out pieces when the slab
+// width is a power of two — the first version spent ~80 instructions per 16-byte piece on divisions and address
+// math and was issue-bound.
 template <bool kSplit, int kGroups>
 __device__ __forceinline__ void wgrad_produce(const WgradParams& p, const int stages, uint8_t* smem, const int stage_bytes,
                                               const int a_part, const int g_part, uint64_t* full_bar, uint64_t* empty_bar,
@@ -565,64 +697,100 @@ __device__ __forceinline__ void wgrad_produce(const WgradParams& p, const int st
   constexpr int kWarpsPerGroup = kProducerWarps / kGroups;
   constexpr int kGroupThreads = kWarpsPerGroup * 32;
   constexpr int kPiecesA = (kWgRows * 32) / kGroupThreads;  // 16-byte pieces of the A tile per thread
+  constexpr int kRowStepA = kGroupThreads / 32;             // rows between consecutive A pieces of a thread
+  constexpr int kBatch = 8;                                  // grad_out pieces per thread per batch
   const int gidx = warp / kWarpsPerGroup;
   const int tg = (warp % kWarpsPerGroup) * 32 + lane;
   const int pg = p.n_pad / 4;  // 16-byte pieces per grad_out row slab (padded)
+  int pg_shift = -1;
+  for (int sft = 3; sft <= 6; ++sft)
+    if ((1 << sft) == pg) pg_shift = sft;
+  const bool g_fast = pg_shift >= 0 && pg <= kGroupThreads;  // then a thread's pieces all sit in one 16-byte column
   const int co0 = static_cast<int>(blockIdx.y) * p.n_pad;  // first output channel of this CTA's slab
   const int flat_m = p.taps * p.c_in;
   const int spi = static_cast<int>(p.rows_per_chunk / kWgRows);  // stage slots per item
   const int my_items = (p.num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const int64_t total = static_cast<int64_t>(my_items) * spi;
+  const int g_total = kWgRows * pg;
+
+  // A pieces of this thread: column piece pcA (fixed), rows rA0 + i * kRowStepA
+  const int pcA = tg & 31, rA0 = tg >> 5;
+  uint32_t offA[kPiecesA];
+#pragma unroll
+  for (int i = 0; i < kPiecesA; ++i)
+    offA[i] = static_cast<uint32_t>(pcA >> 3) * (kWgRows * 128) + mn_piece_offset(rA0 + i * kRowStepA, pcA);
+  // grad_out pieces (fast path): column piece pcG (fixed), rows rG0 + j * rows_per_pass
+  const int pcG = g_fast ? (tg & (pg - 1)) : 0;
+  const int rG0 = g_fast ? (tg >> pg_shift) : 0;
+  const int rStepG = g_fast ? (kGroupThreads >> pg_shift) : 1;
+  const bool colG_ok = co0 + pcG * 4 < p.c_out;
+  const uint32_t offG_col = static_cast<uint32_t>(pcG >> 3) * (kWgRows * 128);
+
+  int cur_item = -1, tap = 0, ci = 0, g = 0;
+  bool a_col_ok = false;
+  int64_t row_begin = 0, row_end = 0;
+  // stage cursor without divisions: gs = it * spi + sl
+  int it = 0, sl = gidx;
+  while (sl >= spi && it < my_items) {
+    sl -= spi;
+    ++it;
+  }
   for (int64_t gs = gidx; gs < total; gs += kGroups) {
-    const int it = static_cast<int>(gs / spi);
-    const int sl = static_cast<int>(gs - static_cast<int64_t>(it) * spi);
-    const int item = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
-    const int g = item % p.groups;
-    const int64_t row_begin = static_cast<int64_t>(item / p.groups) * p.rows_per_chunk;
-    int64_t row_end = row_begin + p.rows_per_chunk;
-    if (row_end > p.num_out) row_end = p.num_out;
+    if (it != cur_item) {
+      cur_item = it;
+      const int item = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+      g = item % p.groups;
+      row_begin = static_cast<int64_t>(item / p.groups) * p.rows_per_chunk;
+      row_end = row_begin + p.rows_per_chunk;
+      if (row_end > p.num_out) row_end = p.num_out;
+      const int flat = g * 128 + pcA * 4;
+      a_col_ok = flat < flat_m;
+      tap = flat / p.c_in;
+      ci = flat - tap * p.c_in;
+    }
     const int64_t rb = row_begin + static_cast<int64_t>(sl) * kWgRows;
     const int stage = static_cast<int>(gs % stages);
     const uint32_t phase = static_cast<uint32_t>((gs / stages) & 1);
 
     // ---- A: 32 rows x 32 pieces
     int32_t src[kPiecesA];
-    int ci_of[kPiecesA];
 #pragma unroll
     for (int i = 0; i < kPiecesA; ++i) {
-      const int e = i * kGroupThreads + tg;
-      const int r = e >> 5, pc = e & 31;
-      const int flat = g * 128 + pc * 4;
-      const int64_t row = rb + r;
+      const int64_t row = rb + rA0 + i * kRowStepA;
       src[i] = -1;
-      ci_of[i] = 0;
-      if (flat < flat_m && row < row_end) {
-        const int tap = flat / p.c_in;
-        ci_of[i] = flat - tap * p.c_in;
-        src[i] = p.nbr ? __ldg(p.nbr + row * p.taps + tap) : static_cast<int32_t>(row);
-      }
+      if (a_col_ok && row < row_end) src[i] = p.nbr ? __ldg(p.nbr + row * p.taps + tap) : static_cast<int32_t>(row);
     }
     float4 va[kPiecesA];
 #pragma unroll
     for (int i = 0; i < kPiecesA; ++i) {
       va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (src[i] >= 0) va[i] = __ldg(reinterpret_cast<const float4*>(p.in + static_cast<int64_t>(src[i]) * p.c_in + ci_of[i]));
+      if (src[i] >= 0) va[i] = __ldg(reinterpret_cast<const float4*>(p.in + static_cast<int64_t>(src[i]) * p.c_in + ci));
     }
     // grad_out rows: the first batch of loads is issued together with the A gathers (one memory latency for the
     // whole stage instead of one per batch); wider slabs need further batches
-    constexpr int kBatch = 8;
-    const int g_total = kWgRows * pg;
     float4 vg[kBatch];
     auto load_g = [&](int e0) {
+      if (g_fast) {
+        const int r_first = rG0 + (e0 >> pg_shift);
 #pragma unroll
-      for (int i = 0; i < kBatch; ++i) {
-        const int e = e0 + i * kGroupThreads + tg;
-        vg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e < g_total) {
-          const int r = e / pg, pc = e - r * pg;
+        for (int i = 0; i < kBatch; ++i) {
+          const int r = r_first + i * rStepG;
           const int64_t row = rb + r;
-          if (row < row_end && co0 + pc * 4 < p.c_out)
-            vg[i] = __ldg(reinterpret_cast<const float4*>(p.gout + row * p.c_out + co0 + pc * 4));
+          vg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < kWgRows && row < row_end && colG_ok)
+            vg[i] = __ldg(reinterpret_cast<const float4*>(p.gout + row * p.c_out + co0 + pcG * 4));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i) {
+          const int e = e0 + i * kGroupThreads + tg;
+          vg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (e < g_total) {
+            const int r = e / pg, pc = e - r * pg;
+            const int64_t row = rb + r;
+            if (row < row_end && co0 + pc * 4 < p.c_out)
+              vg[i] = __ldg(reinterpret_cast<const float4*>(p.gout + row * p.c_out + co0 + pc * 4));
+          }
         }
       }
     };
@@ -633,25 +801,36 @@ __device__ __forceinline__ void wgrad_produce(const WgradParams& p, const int st
     uint8_t* g_hi = a_hi + kParts * a_part;
     uint8_t* g_lo = g_hi + g_part;
 #pragma unroll
-    for (int i = 0; i < kPiecesA; ++i) {
-      const int e = i * kGroupThreads + tg;
-      const int r = e >> 5, pc = e & 31;
-      split_store(a_hi, a_lo, static_cast<uint32_t>(pc >> 3) * (kWgRows * 128) + mn_piece_offset(r, pc), va[i], kSplit);
-    }
+    for (int i = 0; i < kPiecesA; ++i) split_store(a_hi, a_lo, offA[i], va[i], kSplit);
     for (int e0 = 0; e0 < g_total; e0 += kGroupThreads * kBatch) {
       if (e0 > 0) load_g(e0);
+      if (g_fast) {
+        const int r_first = rG0 + (e0 >> pg_shift);
 #pragma unroll
-      for (int i = 0; i < kBatch; ++i) {
-        const int e = e0 + i * kGroupThreads + tg;
-        if (e < g_total) {
-          const int r = e / pg, pc = e - r * pg;
-          split_store(g_hi, g_lo, static_cast<uint32_t>(pc >> 3) * (kWgRows * 128) + mn_piece_offset(r, pc), vg[i], kSplit);
+        for (int i = 0; i < kBatch; ++i) {
+          const int r = r_first + i * rStepG;
+          if (r < kWgRows) split_store(g_hi, g_lo, offG_col + mn_piece_offset(r, pcG), vg[i], kSplit);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i) {
+          const int e = e0 + i * kGroupThreads + tg;
+          if (e < g_total) {
+            const int r = e / pg, pc = e - r * pg;
+            split_store(g_hi, g_lo, static_cast<uint32_t>(pc >> 3) * (kWgRows * 128) + mn_piece_offset(r, pc), vg[i], kSplit);
+          }
         }
       }
     }
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
+    // advance the (item, slot) cursor by kGroups stages
+    sl += kGroups;
+    while (sl >= spi) {
+      sl -= spi;
+      ++it;
+    }
   }
 }
 
@@ -899,8 +1078,19 @@ extern "C" int efgb_spconv_tc_forward(const float* in_feats, int64_t num_in, int
   p.sa = (budget - p.sb * b_bytes) / a_bytes;
   if (p.sa > 6) p.sa = 6;
   EFGB_REQUIRE(p.sa >= 2, EFGB_EINVAL, "spconv_tc_forward: tile does not fit shared memory");
+  {
+    // EFGB_TC_PRODUCER=async selects the cp.async producers (need >= 3 A stages).  Measured on B200 they are ~20 %
+    // SLOWER than the register-staged ones on the sparse layers (96 vs 77 us at C=16, 184 vs 147 us at C=64) and equal
+    // on the dense ones: the stage rate is bound by shared-memory bandwidth (SS-mode tcgen05.mma re-reads A and B
+    // from shared memory for each of the three split products), and the in-place split adds a read + a write per piece.
+    const char* prod = getenv("EFGB_TC_PRODUCER");
+    p.async_gather = (p.sa >= 3 && prod && strcmp(prod, "async") == 0) ? 1 : 0;
+    p.cred_shift = -1;
+    for (int sft = 2; sft < 16; ++sft)
+      if ((1 << sft) == c_red) p.cred_shift = sft;
+  }
   const size_t smem = 1024 + static_cast<size_t>(p.sa) * a_bytes + static_cast<size_t>(p.sb) * b_bytes +
-                      (2 * p.sa + 2 * p.sb + 4) * 8 + 16;
+                      (3 * p.sa + 2 * p.sb + 4) * 8 + 16;
   int gx = kNumSMs / n_split;
   if (gx < 1) gx = 1;
   if (gx > p.num_super) gx = p.num_super;

@@ -121,7 +121,9 @@ class ConQueR(VoxelDETR):
         nq = self.num_queries
         prop, head = self.transformer.proposal_head, self.transformer.decoder.detection_head
         num_boxes = prop.losses.normaliser(targets, cls_out.device)
-        enc_cls, enc_box = prop(memory, anchors)
+        cached = getattr(self.transformer, "_enc_head_out", None)  # see VoxelDETR.losses
+        enc_cls, enc_box = cached if cached is not None else prop(memory, anchors)
+        self.transformer._enc_head_out = None
         bin_targets = TargetList(dict(t, labels=torch.zeros_like(t["labels"])) for t in targets)
         bin_targets.labels_cat = torch.zeros_like(targets.labels_cat)
         bin_targets.boxes_cat, bin_targets.offsets = targets.boxes_cat, targets.offsets

@@ -61,9 +61,13 @@ class Det3DHead(nn.Module):
         boxes = (self.bbox_embed[layer_idx](embed) + inverse_sigmoid(anchors)).sigmoid()
         return logits, boxes
 
-    def compute_losses(self, outputs, targets, num_boxes=None, solved=None):
+    def compute_losses(self, outputs, targets, num_boxes=None, solved=None, stacked=None):
+        """stacked = (logits [L,B,Q,C], boxes [L,B,Q,7]) selects the all-layers-at-once evaluation
+        (Det3DLoss.finish_stacked); ``outputs`` is then only used for its keys."""
         if solved is None:
             loss_dict = self.losses(outputs, targets, num_boxes)
+        elif stacked is not None:
+            loss_dict = self.losses.finish_stacked(stacked[0], stacked[1], targets, solved, num_boxes)
         else:
             loss_dict = self.losses.finish(outputs, targets, solved, num_boxes)
         weights = self.losses.weight_dict

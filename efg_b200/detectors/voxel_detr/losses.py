@@ -156,6 +156,46 @@ class Det3DLoss(nn.Module):
             mats.extend(self.matcher.cost_matrices(lo, targets))
         return mats
 
+    def finish_stacked(self, logits, boxes, targets, solved, num_boxes):
+        """Losses of ALL decoder layers in one pass.  logits [L,B,Q,C], boxes [L,B,Q,7]; solved: L MatchIndex
+        objects (device).  Same elementwise expressions as ``finish`` (ClassificationLoss / RegressionLoss layer by
+        layer, VD/losses.py:11-96) evaluated on the layer-stacked tensors, followed by per-layer sums — L-fold fewer
+        kernel launches in the launch-bound tail of the step.  Keys and suffixes as in ``finish``."""
+        L = logits.shape[0]
+        n = solved[0].batch.numel()
+        assert all(m.batch.numel() == n for m in solved), "every layer matches the same ground truth"
+        dev = logits.device
+        layer = torch.arange(L, device=dev).repeat_interleave(n)
+        b_idx = torch.cat([m.batch for m in solved])
+        s_idx = torch.cat([m.src for m in solved])
+        t_idx = torch.cat([m.tgt for m in solved])
+        out = {}
+        for loss in self.losses:
+            if loss == "focal_labels":
+                tgt_cls = targets.labels_cat[t_idx]
+                onehot = torch.zeros_like(logits)
+                onehot.index_put_((layer, b_idx, s_idx, tgt_cls), onehot.new_ones(()))
+                focal = sigmoid_focal_loss(logits, onehot, alpha=self.det3d_losses[loss].focal_alpha, gamma=2.0,
+                                           reduction="none")
+                out["loss_ce"] = focal.sum((1, 2, 3)) / num_boxes
+                # what get_target_classes() reports: the matched logits / classes of the LAST layer
+                self.det3d_losses[loss].src_logits = logits[L - 1][solved[-1].batch, solved[-1].src]
+                self.det3d_losses[loss].target_classes = tgt_cls[(L - 1) * n:]
+            else:
+                src = boxes[layer, b_idx, s_idx]
+                tgt = targets.boxes_cat[t_idx]
+                src_box, src_rad = src.split(6, dim=-1)
+                tgt_box, tgt_rad = tgt.split(6, dim=-1)
+                giou = generalized_box3d_iou_paired(cxcyczlwh_to_corners(src_box), cxcyczlwh_to_corners(tgt_box))
+                out["loss_bbox"] = F.l1_loss(src_box, tgt_box, reduction="none").view(L, -1).sum(1) / num_boxes
+                out["loss_giou"] = (1 - giou).view(L, -1).sum(1) / num_boxes
+                out["loss_rad"] = F.l1_loss(src_rad, tgt_rad, reduction="none").view(L, -1).sum(1) / num_boxes
+        losses = {}
+        for k, vec in out.items():
+            for li in range(L):
+                losses[k + ("" if li == L - 1 else "_{}".format(li))] = vec[li]
+        return losses
+
     def finish(self, outputs, targets, solved, num_boxes):
         """solved: per layer, either a MatchIndex (device) or a list of per-scene (src, tgt) CPU pairs."""
         layers = self.layers_of(outputs)

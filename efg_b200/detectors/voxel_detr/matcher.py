@@ -40,6 +40,30 @@ class HungarianMatcher3d(nn.Module):
         return mats
 
     @torch.no_grad()
+    def cost_matrices_stacked(self, logits, boxes, targets):
+        """The same cost matrices for ALL decoder layers at once: logits [L,B,Q,C], boxes [L,B,Q,7] ->
+        list in layer-major, scene-minor order (what ``cost_matrices`` gives layer by layer).  Every entry is
+        computed by the same elementwise / pairwise expressions on the same operands, so the matrices — and
+        therefore the assignments — are identical; only the number of kernel launches drops L-fold."""
+        L, B, Q = logits.shape[:3]
+        prob = logits.float().sigmoid()
+        alpha, gamma = 0.25, 2.0
+        neg = (1 - alpha) * (prob ** gamma) * (-(1 - prob + 1e-8).log())
+        pos = alpha * ((1 - prob) ** gamma) * (-(prob + 1e-8).log())
+        cls_cost = pos - neg
+        per_scene = []
+        for i, tgt in enumerate(targets):
+            tb = tgt["gt_boxes"].float()
+            box6 = boxes[:, i, :, :6].float().reshape(L * Q, 6)
+            rad = boxes[:, i, :, 6:].float().reshape(L * Q, -1)
+            c = self.cost_bbox * torch.cdist(box6, tb[:, :6], p=1)
+            c = c + self.cost_class * cls_cost[:, i].reshape(L * Q, -1)[:, tgt["labels"]]
+            c = c - self.cost_giou * generalized_box3d_iou(cxcyczlwh_to_corners(box6), cxcyczlwh_to_corners(tb[:, :6]))
+            c = c + self.cost_rad * torch.cdist(rad, tb[:, 6:], p=1)
+            per_scene.append(c.view(L, Q, -1))
+        return [per_scene[i][l] for l in range(L) for i in range(B)]
+
+    @torch.no_grad()
     def forward(self, outputs, targets):
         mats = self.cost_matrices(outputs, targets)
         return self.solve(mats)

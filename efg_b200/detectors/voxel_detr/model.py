@@ -59,6 +59,7 @@ class VoxelDETR(nn.Module):
         self.num_classes = len(config.dataset.classes)
         self.num_queries = config.model.transformer.num_queries
         self.config = config
+        self.stacked_losses = True  # decoder-layer losses / matching costs evaluated on layer-stacked tensors
 
         input_dim = len(config.dataset.format) if config.dataset.nsweeps == 1 else len(config.dataset.format) + 1
         self.input_dim = input_dim
@@ -213,21 +214,32 @@ class VoxelDETR(nn.Module):
         losses = {}
         prop, head = self.transformer.proposal_head, self.transformer.decoder.detection_head
         num_boxes = prop.losses.normaliser(targets, cls_out.device)
-        enc_cls, enc_box = prop(memory, anchors)
+        # the reference evaluates the proposal head twice on the same (memory, anchors) — once, detached, to pick the
+        # top-k proposals (VD/transformer.py:56) and once for this loss (VD/voxel_detr.py:145); the transformer keeps
+        # the first result, which is the same tensor with its graph attached
+        cached = getattr(self.transformer, "_enc_head_out", None)
+        enc_cls, enc_box = cached if cached is not None else prop(memory, anchors)
+        self.transformer._enc_head_out = None
         bin_targets = TargetList(dict(t, labels=torch.zeros_like(t["labels"])) for t in targets)
         bin_targets.labels_cat = torch.zeros_like(targets.labels_cat)
         bin_targets.boxes_cat, bin_targets.offsets = targets.boxes_cat, targets.offsets
         enc_out = {"topk_indexes": topk_idx, "pred_logits": enc_cls, "pred_boxes": enc_box}
         dec_out = {"pred_logits": cls_out[-1], "pred_boxes": box_out[-1],
                    "aux_outputs": [{"pred_logits": a, "pred_boxes": b} for a, b in zip(cls_out[:-1], box_out[:-1])]}
-        mats = prop.losses.prepare(enc_out, bin_targets) + head.losses.prepare(dec_out, targets)
+        stacked = self.stacked_losses and isinstance(targets, TargetList) and targets.labels_cat is not None
+        if stacked:
+            dec_mats = head.losses.matcher.cost_matrices_stacked(cls_out, box_out, targets)
+        else:
+            dec_mats = head.losses.prepare(dec_out, targets)
+        mats = prop.losses.prepare(enc_out, bin_targets) + dec_mats
         solved = head.losses.matcher.solve(mats)  # the one host round trip of the loss
         bs = len(targets)
         per_layer = [solved[i * bs:(i + 1) * bs] for i in range(len(solved) // max(bs, 1))]
         matches = upload_matches(per_layer, targets.offsets, cls_out.device)
         enc = prop.compute_losses(enc_out, bin_targets, num_boxes, solved=matches[:1])
         losses.update({k + "_enc": v for k, v in enc.items()})
-        losses.update(head.compute_losses(dec_out, targets, num_boxes, solved=matches[1:]))
+        losses.update(head.compute_losses(dec_out, targets, num_boxes, solved=matches[1:],
+                                          stacked=(cls_out, box_out) if stacked else None))
         return losses
 
     def postprocess(self, logits, boxes):

@@ -138,6 +138,7 @@ class Transformer(nn.Module):
         self.decoder = TransformerDecoder(d_model, dec, num_decoder_layers)
         self.proposal_head = None  # attached by the detector
         self._ref_cache = {}
+        self._enc_head_out = None  # (logits, windows) of the proposal head, reused by the encoder loss
 
     def _create_ref_windows(self, tensor_list):
         """One (cx, cy, 0.5, 0.025, 0.025, 0.5, 0) window per BEV cell (VD/transformer.py:30-52)."""
@@ -157,6 +158,7 @@ class Transformer(nn.Module):
 
     def _get_enc_proposals(self, enc_embed, ref_windows):
         logits, windows = self.proposal_head(enc_embed, ref_windows)
+        self._enc_head_out = (logits, windows) if self.training and torch.is_grad_enabled() else None
         probs = logits[..., 0].sigmoid()
         # The reference takes topk(sorted=False): which of several EQUAL scores survive, and in which order,
         # is unspecified (empty BEV cells produce bit-identical scores).  Canonical choice here: a stable

@@ -180,3 +180,41 @@ def test_centerpoint_label_assignment_heatmap():
     y, x = divmod(int(t["ind"][0][0]), 32)
     assert hm[0, y, x] == 1.0  # the peak sits on the object's centre cell
     assert np.allclose(t["anno_box"][0][0, 3:6], np.log([4.0, 2.0, 1.5]), atol=1e-6)
+
+
+def test_stacked_losses_equal_per_layer_reference_path():
+    """Evaluating matching costs and losses of all decoder layers on layer-stacked tensors (and reusing the
+    proposal head's output for the encoder loss) is the reference's layer-by-layer evaluation
+    (VD/losses.py:98-141, VD/voxel_detr.py:141-166) with fewer kernel launches: same losses, same gradients."""
+    torch.manual_seed(3)
+    cfg = small_config()
+    ref = VoxelDETR(cfg, backend=cpu_backend())
+    fast = VoxelDETR(cfg, backend=cpu_backend())
+    fast.load_state_dict(ref.state_dict())
+    ref.stacked_losses = False
+    ref.train()
+    fast.train()
+    batch = [(voxelized_sample(p, cfg.dataset), {"annotations": a}) for p, a in small_batch(2, 4000, seed=11)]
+    out = []
+    for m in (ref, fast):
+        if m is ref:  # the reference path evaluates the proposal head a second time
+            orig = m.transformer._get_enc_proposals
+
+            def no_cache(*a, _orig=orig, _m=m, **k):
+                r = _orig(*a, **k)
+                _m.transformer._enc_head_out = None
+                return r
+
+            m.transformer._get_enc_proposals = no_cache
+        losses = m(batch)
+        total = sum(v for k, v in losses.items() if k.startswith("loss"))
+        total.backward()
+        out.append((losses, {n: p.grad for n, p in m.named_parameters() if p.grad is not None}))
+    (l0, g0), (l1, g1) = out
+    assert set(l0) == set(l1)
+    for k in l0:
+        assert abs(float(l0[k]) - float(l1[k])) <= 1e-5 * max(1.0, abs(float(l0[k]))), (k, float(l0[k]), float(l1[k]))
+    assert set(g0) == set(g1)
+    for n in g0:
+        scale = max(1.0, g0[n].abs().max().item())
+        assert (g0[n] - g1[n]).abs().max().item() <= 2e-4 * scale, n
