@@ -21,7 +21,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -66,54 +65,65 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: once per step, right after the step has
+    been enqueued (the GPU is then still executing it — the host runs ahead of the device), through NVML in-process.
+    A polling `nvidia-smi -lms 100` subprocess was measured to slow the (partly launch-bound) step by ~15 %
+    through driver-lock contention, so it is only the fallback when NVML is unavailable."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
         self.index = index
-        self.proc = None
-        self.lines = []
-
-    def start(self):
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.nvml = None
+        self.handle = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].strip().isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
         except Exception:
-            self.proc = None
+            self.nvml = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+    def sample(self):
+        if self.nvml is None:
+            return self._sample_smi()
+        n = self.nvml
         try:
-            self.proc.wait(timeout=2)
+            self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+            self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
+            get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+            mask = int(get(self.handle))
+            for bit, name in self.REASONS:
+                if mask & bit:
+                    self.reasons.add(name)
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 8:
-                continue
-            try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
+            pass
+
+    def _sample_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=5).stdout.strip().splitlines()[0]
+            parts = [p.strip() for p in out.split(",")]
+            self.sm.append(float(parts[0]))
+            self.mx.append(float(parts[1]))
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[2:6]):
                 if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def result(self):
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (NVML and nvidia-smi unavailable)"]}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": max(self.mx), "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "how": "NVML, one sample per timed step while the step executes" if self.nvml
+                else "nvidia-smi, one sample per timed step"}
 
 
 def kernel_of(family):
@@ -205,23 +215,27 @@ def run_efgb200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(batches, steps, from_host):
+    def timed(batches, steps, from_host, sampler=None):
+        """EXACTLY `steps` steps between one pair of CUDA events, bracketed by barrier + synchronize on both sides.
+        L2 is flushed before every step (a 256 MiB memset inside the timed span, ~0.04 ms).  With host inputs every
+        step copies its pinned point clouds to the device and reads its loss back (a full pipeline drain per step)."""
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ms = 0.0
         last = None
+        barrier()
+        ev0.record()
         for i in range(steps):
-            l2_flush.zero_()  # flush L2 between timed iterations (outside the timed span)
+            l2_flush.zero_()
             b = batches[i % len(batches)]
-            barrier()
-            ev0.record()
             if from_host:
                 b = [(t.to(dev, non_blocking=True), a) for t, a in b]
             total = step(b)
+            if sampler is not None:
+                sampler.sample()  # the device is still executing this step
             if from_host:
                 last = float(total.item())  # D2H read of the step's result
-            ev1.record()
-            torch.cuda.synchronize()
-            ms += ev0.elapsed_time(ev1)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -242,11 +256,9 @@ def run_efgb200(args):
         return
 
     launches0 = _lib.lib().efgb_launch_count()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ms_dev, _ = timed(resident, args.steps, from_host=False)
-    clocks = sampler.stop() if rank == 0 else None
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_dev, _ = timed(resident, args.steps, from_host=False, sampler=sampler)
+    clocks = sampler.result() if rank == 0 else None
     launches = _lib.lib().efgb_launch_count() - launches0
     ms_e2e, last_loss = timed(pinned, args.steps, from_host=True)
 
@@ -315,7 +327,7 @@ def run_efgb200(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "scenes_per_gpu": args.scenes, "points_per_scene": args.points,
                    "num_queries": NUM_QUERIES, "grid": "1504x1504x40", "step": "voxelize+fwd+bwd+allreduce+adamw",
-                   "cuda_graph": "encoder fwd+bwd" if args.graph else "none", "parallelism": "dp%d" % world, "l2": "flushed between timed iterations (256 MiB memset)"},
+                   "cuda_graph": "encoder fwd+bwd" if args.graph else "none", "parallelism": "dp%d" % world, "l2": "flushed before every timed step (256 MiB memset, inside the timed span)"},
         "e2e": {"value": round(e2e_value, 3), "unit": "scenes/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": last_loss},
         "gpu_launches": int(launches),

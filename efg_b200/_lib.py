@@ -48,6 +48,8 @@ SIGNATURES = {
     "efgb_spconv_wgrad": (_int, [_vp, _i64, _int, _vp, _vp, _i64, _int, _int, _vp, _vp]),
     "efgb_sparse_to_dense": (_int, [_vp, _vp, _i64, _int, _int, _host_i32x3, _vp, _vp]),
     "efgb_dense_to_sparse": (_int, [_vp, _vp, _i64, _int, _int, _host_i32x3, _vp, _vp]),
+    "efgb_lsa_batched": (_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+                                ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64), _int, _vp, _vp, _vp]),
     "efgb_colsum_workspace_bytes": (_sz, [_i64, _int]),
     "efgb_colsum": (_int, [_vp, _i64, _int, _vp, _vp, _sz, _vp]),
     "efgb_box_attn_forward": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _int, _vp, _vp]),

@@ -57,6 +57,28 @@ def upload_matches(solved_layers, offsets, device):
     return out
 
 
+def device_matches(mats, num_layers, offsets, device):
+    """The assignments of every layer solved ON THE DEVICE (efg_b200.ops.lsa_batched — scipy's algorithm and
+    tie-breaking, csrc/lsa.cu): no device-to-host copy of the cost matrices, no pipeline drain.  ``mats`` in
+    layer-major, scene-minor order; returns one MatchIndex per layer.  The batch index and the ground-truth
+    offsets of the pairs depend only on the (host-known) matrix shapes."""
+    from ... import ops
+
+    rows, cols, sizes = ops.lsa_batched(mats)
+    bs = len(mats) // max(num_layers, 1)
+    per_layer = sizes[:bs]
+    n = sum(per_layer)
+    b_host = torch.cat([torch.full((k,), i, dtype=torch.int64) for i, k in enumerate(per_layer)]) if n else torch.zeros(0, dtype=torch.int64)
+    o_host = torch.cat([torch.full((k,), offsets[i], dtype=torch.int64) for i, k in enumerate(per_layer)]) if n else torch.zeros(0, dtype=torch.int64)
+    both = torch.stack([b_host, o_host]).pin_memory().to(device, non_blocking=True)
+    out = []
+    for l in range(num_layers):
+        assert sizes[l * bs:(l + 1) * bs] == per_layer
+        seg = slice(l * n, (l + 1) * n)
+        out.append(MatchIndex(both[0], rows[seg], cols[seg] + both[1]))
+    return out
+
+
 class ClassificationLoss(nn.Module):
     def __init__(self, focal_alpha):
         super().__init__()

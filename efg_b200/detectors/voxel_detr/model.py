@@ -60,6 +60,7 @@ class VoxelDETR(nn.Module):
         self.num_queries = config.model.transformer.num_queries
         self.config = config
         self.stacked_losses = True  # decoder-layer losses / matching costs evaluated on layer-stacked tensors
+        self.device_matching = True  # Hungarian assignments on the GPU (no host round trip); False = host scipy
 
         input_dim = len(config.dataset.format) if config.dataset.nsweeps == 1 else len(config.dataset.format) + 1
         self.input_dim = input_dim
@@ -209,7 +210,7 @@ class VoxelDETR(nn.Module):
         decoder layers) are built on the GPU and solved after ONE device-to-host transfer; the assignments
         go back in one pinned non-blocking copy (the reference syncs once per layer and per index tensor,
         VD/modules/matcher.py:86, VD/losses.py:17-48)."""
-        from .losses import TargetList, upload_matches
+        from .losses import TargetList, device_matches, upload_matches
 
         losses = {}
         prop, head = self.transformer.proposal_head, self.transformer.decoder.detection_head
@@ -232,10 +233,15 @@ class VoxelDETR(nn.Module):
         else:
             dec_mats = head.losses.prepare(dec_out, targets)
         mats = prop.losses.prepare(enc_out, bin_targets) + dec_mats
-        solved = head.losses.matcher.solve(mats)  # the one host round trip of the loss
-        bs = len(targets)
-        per_layer = [solved[i * bs:(i + 1) * bs] for i in range(len(solved) // max(bs, 1))]
-        matches = upload_matches(per_layer, targets.offsets, cls_out.device)
+        matcher = head.losses.matcher
+        if self.device_matching and mats and mats[0].is_cuda and "solve" not in matcher.__dict__:
+            # assignments solved on the device (scipy's algorithm, csrc/lsa.cu): the step has no host round trip here
+            matches = device_matches(mats, len(mats) // max(len(targets), 1), targets.offsets, cls_out.device)
+        else:
+            solved = matcher.solve(mats)  # host scipy, one device-to-host transfer (the reference's path)
+            bs = len(targets)
+            per_layer = [solved[i * bs:(i + 1) * bs] for i in range(len(solved) // max(bs, 1))]
+            matches = upload_matches(per_layer, targets.offsets, cls_out.device)
         enc = prop.compute_losses(enc_out, bin_targets, num_boxes, solved=matches[:1])
         losses.update({k + "_enc": v for k, v in enc.items()})
         losses.update(head.compute_losses(dec_out, targets, num_boxes, solved=matches[1:],

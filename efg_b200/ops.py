@@ -358,6 +358,43 @@ def colsum(x2d):
     return out
 
 
+def lsa_batched(mats):
+    """Linear sum assignment of every cost matrix in ``mats`` (CUDA f32 [rows_k, cols_k], unit inner stride) on the
+    device, scipy-identical.  Returns (rows int64 [sum n_k], cols int64 [sum n_k], sizes) with n_k = min(rows_k, cols_k);
+    problem k owns the slice [sum(sizes[:k]), sum(sizes[:k + 1])), pairs sorted by row.  No host synchronisation."""
+    if not mats:
+        return None, None, []
+    dev = mats[0].device
+    count = len(mats)
+    ptrs = (ctypes.c_void_p * count)()
+    rows = (ctypes.c_int32 * count)()
+    cols = (ctypes.c_int32 * count)()
+    lds = (ctypes.c_int32 * count)()
+    offs = (ctypes.c_int64 * count)()
+    sizes, off = [], 0
+    for k, m in enumerate(mats):
+        if not m.is_cuda or m.dtype != torch.float32 or m.dim() != 2:
+            raise RuntimeError("lsa_batched: cost matrices must be 2-D CUDA float32 tensors")
+        if m.numel() and m.stride(1) != 1:
+            raise RuntimeError("lsa_batched: cost matrices need unit inner stride")
+        r, c = m.shape
+        ptrs[k] = m.data_ptr() if m.numel() else None
+        rows[k], cols[k] = r, c
+        lds[k] = max(m.stride(0), c) if r > 1 else max(c, 1)
+        offs[k] = off
+        n = min(r, c)
+        sizes.append(n)
+        off += n
+    out_rows = torch.empty((max(off, 1),), dtype=torch.int64, device=dev)
+    out_cols = torch.empty((max(off, 1),), dtype=torch.int64, device=dev)
+    t0 = PROFILER.begin() if PROFILER is not None else None
+    _lib.check(_lib.lib().efgb_lsa_batched(ptrs, rows, cols, lds, offs, count, _p(out_rows), _p(out_cols), _stream()),
+               "lsa_batched")
+    if t0 is not None:
+        PROFILER.end("lsa", t0, 4 * sum(m.numel() for m in mats) + 16 * off)
+    return out_rows[:off], out_cols[:off], sizes
+
+
 class _DenseLinearFn(torch.autograd.Function):
     """y = x @ W^T + b on the tensor-core gather-GEMM kernels with an identity rulebook (a dense layer is a
     1-tap sparse conv over all rows).  fp32-faithful in "fp32x3" mode; used for the large token-wise linears

@@ -191,6 +191,20 @@ int efgb_dense_to_sparse(const float* dense, const int32_t* coords, int64_t num_
                          int batch, const int32_t* grid_dhw_host3, float* feats, efgb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Linear sum assignment for a batch of small dense cost matrices that live on the device — the Hungarian
+ * matching of HungarianMatcher3d (VD/modules/matcher.py:54-91), which the reference solves on the host
+ * with scipy.optimize.linear_sum_assignment after a blocking copy.  Same algorithm and tie-breaking as
+ * scipy (shortest augmenting paths, double precision), so the assignments are the ones scipy returns.
+ *   problem k: cost matrix rows_host[k] x cols_host[k] f32 at device address cost_ptrs_host[k], row
+ *   stride ld_host[k] floats; writes n_k = min(rows, cols) (row, col) pairs sorted by row to
+ *   out_rows / out_cols + out_offsets_host[k] (device int64).  The *_host arrays are host memory and
+ *   are consumed before the call returns.  Costs must be finite.
+ * ------------------------------------------------------------------------------------------ */
+int efgb_lsa_batched(const void* const* cost_ptrs_host, const int32_t* rows_host,
+                     const int32_t* cols_host, const int32_t* ld_host, const int64_t* out_offsets_host,
+                     int count, int64_t* out_rows, int64_t* out_cols, efgb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Column sums out[c] = sum_r x[r, c] of a row-major [rows, cols] f32 matrix (cols % 4 == 0): the bias
  * gradient of the token-wise linear layers (autograd of F.linear in VD/transformer.py:41-64 and
  * VD/modules/box_attention.py:97-115, i.e. grad_out.sum(0) over B * 35 344 rows).  Deterministic

@@ -13,11 +13,11 @@ env ${ALT_ENV} timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baselin
 echo "alt bench (${ALT_ENV}) rc=$?"; cut -c1-300 gpurun_out/bench_line_alt.json
 fi
 timeout 60 python scripts/bench_box_attn.py > gpurun_out/box_micro.txt 2>&1; cat gpurun_out/box_micro.txt
-EFGB_BOX_ATTN=generic timeout 60 python scripts/bench_box_attn.py > gpurun_out/box_micro_generic.txt 2>&1; cat gpurun_out/box_micro_generic.txt
+timeout 120 python scripts/bench_dense.py > gpurun_out/dense_micro.txt 2>&1; tail -4 gpurun_out/dense_micro.txt
 timeout 120 python scripts/bench_conv.py fp32x3 > gpurun_out/conv_micro.txt 2>&1; tail -9 gpurun_out/conv_micro.txt
-timeout 120 python scripts/prof_step.py > gpurun_out/prof_step.txt 2>&1; head -3 gpurun_out/prof_step.txt
+timeout 150 python scripts/prof_phases.py > gpurun_out/prof_phases.txt 2>&1; head -16 gpurun_out/prof_phases.txt
 if [ "${NONCU:-0}" != "1" ]; then
-timeout 400 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
+timeout 400 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
     python bench.py --profile-step --warmup 3 > gpurun_out/ncu_bench.log 2>&1
 echo "launch list rc=$?"; wc -l gpurun_out/launches.csv
 ITERS=1 WARM=1 timeout 200 ncu --set full --clock-control none --import-source on -k regex:"box_attn" -f -o /tmp/prof_box \
