@@ -75,6 +75,7 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.sm, self.mx, self.reasons = [], [], set()
+        self.cost_ms = []
         self.nvml = None
         self.handle = None
         try:
@@ -89,6 +90,11 @@ class ClockSampler:
             self.nvml = None
 
     def sample(self):
+        t0 = time.perf_counter()
+        self._sample()
+        self.cost_ms.append((time.perf_counter() - t0) * 1e3)
+
+    def _sample(self):
         if self.nvml is None:
             return self._sample_smi()
         n = self.nvml
@@ -122,7 +128,7 @@ class ClockSampler:
         if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (NVML and nvidia-smi unavailable)"]}
         return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": max(self.mx), "reasons": sorted(self.reasons),
-                "samples": len(self.sm), "how": "NVML, one sample per timed step while the step executes" if self.nvml
+                "samples": len(self.sm), "host_ms_per_sample": round(float(np.mean(self.cost_ms)), 3), "how": "NVML, one sample per timed step while the step executes" if self.nvml
                 else "nvidia-smi, one sample per timed step"}
 
 
@@ -256,9 +262,9 @@ def run_efgb200(args):
         return
 
     launches0 = _lib.lib().efgb_launch_count()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if rank == 0 and not os.environ.get("EFGB_BENCH_NO_CLOCKS") else None
     ms_dev, _ = timed(resident, args.steps, from_host=False, sampler=sampler)
-    clocks = sampler.result() if rank == 0 else None
+    clocks = sampler.result() if sampler is not None else None
     launches = _lib.lib().efgb_launch_count() - launches0
     ms_e2e, last_loss = timed(pinned, args.steps, from_host=True)
 
