@@ -21,6 +21,7 @@ import json
 import os
 import subprocess
 import sys
+import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -65,19 +66,23 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region: once per step, right after the step has
-    been enqueued (the GPU is then still executing it — the host runs ahead of the device), through NVML in-process.
-    A polling `nvidia-smi -lms 100` subprocess was measured to slow the (partly launch-bound) step by ~15 %
-    through driver-lock contention, so it is only the fallback when NVML is unavailable."""
+    """SM clock and throttle reasons sampled DURING the timed region by a background thread through NVML (in-process;
+    the NVML calls release the GIL, so the enqueueing thread is not held up), a few samples per second.
+    Why not the recipe's `nvidia-smi -lms 100` subprocess: on this pool one NVML clock/reason query takes 4-24 ms of
+    host time, and a 10 Hz poll (or a blocking query after every step) slowed the partly launch-bound step by 15-40 %
+    (measured: 57-68 ms per step with, 47 ms without).  nvidia-smi is only the fallback when NVML is unavailable."""
 
     REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
-    def __init__(self, index):
+    def __init__(self, index, period_s=0.2):
         self.index = index
-        self.sm, self.mx, self.reasons = [], [], set()
-        self.cost_ms = []
+        self.period = period_s
+        self.sm, self.reasons, self.cost_ms = [], set(), []
+        self.max_mhz = None
         self.nvml = None
         self.handle = None
+        self._stop = threading.Event()
+        self._thread = None
         try:
             import pynvml
 
@@ -86,28 +91,26 @@ class ClockSampler:
             visible = os.environ.get("CUDA_VISIBLE_DEVICES")
             phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].strip().isdigit() else index
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
         except Exception:
             self.nvml = None
 
     def sample(self):
         t0 = time.perf_counter()
-        self._sample()
+        if self.nvml is not None:
+            n = self.nvml
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+                mask = int(get(self.handle))
+                for bit, name in self.REASONS:
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+        else:
+            self._sample_smi()
         self.cost_ms.append((time.perf_counter() - t0) * 1e3)
-
-    def _sample(self):
-        if self.nvml is None:
-            return self._sample_smi()
-        n = self.nvml
-        try:
-            self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
-            self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
-            get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
-            mask = int(get(self.handle))
-            for bit, name in self.REASONS:
-                if mask & bit:
-                    self.reasons.add(name)
-        except Exception:
-            pass
 
     def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -117,19 +120,38 @@ class ClockSampler:
                                  capture_output=True, text=True, timeout=5).stdout.strip().splitlines()[0]
             parts = [p.strip() for p in out.split(",")]
             self.sm.append(float(parts[0]))
-            self.mx.append(float(parts[1]))
+            self.max_mhz = float(parts[1])
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[2:6]):
                 if val.lower().startswith("active"):
                     self.reasons.add(name)
         except Exception:
             pass
 
+    def _run(self):
+        while not self._stop.wait(self.period):
+            self.sample()
+
+    def start(self):
+        """Call right before the timed region (the first sample is taken one period in)."""
+        self._stop.clear()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        """Call after the last step has been ENQUEUED and before the closing synchronize: takes one more sample while
+        the device is still executing, then ends the thread."""
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=10)
+        if not self.sm:
+            self.sample()
+
     def result(self):
         if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (NVML and nvidia-smi unavailable)"]}
-        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": max(self.mx), "reasons": sorted(self.reasons),
-                "samples": len(self.sm), "host_ms_per_sample": round(float(np.mean(self.cost_ms)), 3), "how": "NVML, one sample per timed step while the step executes" if self.nvml
-                else "nvidia-smi, one sample per timed step"}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "host_ms_per_sample": round(float(np.mean(self.cost_ms)), 3),
+                "how": ("NVML" if self.nvml else "nvidia-smi") + " from a background thread every %.0f ms during the timed region" % (self.period * 1e3)}
 
 
 def kernel_of(family):
@@ -228,6 +250,8 @@ def run_efgb200(args):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         last = None
         barrier()
+        if sampler is not None:
+            sampler.start()
         ev0.record()
         for i in range(steps):
             l2_flush.zero_()
@@ -235,11 +259,11 @@ def run_efgb200(args):
             if from_host:
                 b = [(t.to(dev, non_blocking=True), a) for t, a in b]
             total = step(b)
-            if sampler is not None:
-                sampler.sample()  # the device is still executing this step
             if from_host:
                 last = float(total.item())  # D2H read of the step's result
         ev1.record()
+        if sampler is not None:
+            sampler.stop()  # the device is still executing the tail of the last step
         barrier()
         ms = ev0.elapsed_time(ev1)
         if world > 1:

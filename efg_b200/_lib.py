@@ -43,6 +43,7 @@ SIGNATURES = {
     "efgb_spconv_tc_packed_bytes": (_sz, [_int, _int, _int, _int]),
     "efgb_spconv_tc_pack": (_int, [_vp, _int, _int, _int, _int, _int, _vp, _vp]),
     "efgb_spconv_tc_forward": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp]),
+    "efgb_spconv_tc_forward_ex": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _vp, _vp]),
     "efgb_spconv_tc_wgrad_supported": (_int, [_int, _int, _int]),
     "efgb_spconv_tc_wgrad": (_int, [_vp, _i64, _int, _vp, _vp, _i64, _int, _int, _int, _vp, _vp]),
     "efgb_spconv_wgrad": (_int, [_vp, _i64, _int, _vp, _vp, _i64, _int, _int, _vp, _vp]),
@@ -50,6 +51,10 @@ SIGNATURES = {
     "efgb_dense_to_sparse": (_int, [_vp, _vp, _i64, _int, _int, _host_i32x3, _vp, _vp]),
     "efgb_lsa_batched": (_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
                                 ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64), _int, _vp, _vp, _vp]),
+    "efgb_add_layernorm_supported": (_int, [_int]),
+    "efgb_add_layernorm_workspace_bytes": (_sz, [_i64, _int]),
+    "efgb_add_layernorm_forward": (_int, [_vp, _vp, _vp, _vp, _i64, _int, ctypes.c_float, _vp, _vp, _vp, _vp, _vp]),
+    "efgb_add_layernorm_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
     "efgb_colsum_workspace_bytes": (_sz, [_i64, _int]),
     "efgb_colsum": (_int, [_vp, _i64, _int, _vp, _vp, _sz, _vp]),
     "efgb_box_attn_forward": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _int, _vp, _vp]),

@@ -130,6 +130,7 @@ struct Params {
   const float* in;       // [num_in, c_red]
   const float* packed;   // [chunks][parts][n_out][32] swizzled image
   const float* bias;     // [n_out] or null
+  int relu;              // epilogue applies max(x, 0) after the bias
   const int32_t* nbr;    // [num_out, taps], or null = identity (dense GEMM: taps == 1, src row = out row)
   float* out;            // [num_out, n_out]
   int64_t num_out;
@@ -561,6 +562,12 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p) 
               o.y = __uint_as_float(r[j + 1]) + (p.bias ? p.bias[n0 + c0 + j + 1] : 0.f);
               o.z = __uint_as_float(r[j + 2]) + (p.bias ? p.bias[n0 + c0 + j + 2] : 0.f);
               o.w = __uint_as_float(r[j + 3]) + (p.bias ? p.bias[n0 + c0 + j + 3] : 0.f);
+              if (p.relu) {
+                o.x = fmaxf(o.x, 0.f);
+                o.y = fmaxf(o.y, 0.f);
+                o.z = fmaxf(o.z, 0.f);
+                o.w = fmaxf(o.w, 0.f);
+              }
               *reinterpret_cast<float4*>(dst + j) = o;
             }
           }
@@ -1020,9 +1027,20 @@ extern "C" int efgb_spconv_tc_pack(const float* w_param, int c_out, int taps, in
   return EFGB_OK;
 }
 
+extern "C" int efgb_spconv_tc_forward_ex(const float* in_feats, int64_t num_in, int c_red, const float* packed,
+                                         const float* bias, const int32_t* nbr, int64_t num_out, int taps, int n_out,
+                                         int split, int relu, float* out_feats, efgb_stream_t stream_);
+
 extern "C" int efgb_spconv_tc_forward(const float* in_feats, int64_t num_in, int c_red, const float* packed,
                                       const float* bias, const int32_t* nbr, int64_t num_out, int taps, int n_out,
                                       int split, float* out_feats, efgb_stream_t stream_) {
+  return efgb_spconv_tc_forward_ex(in_feats, num_in, c_red, packed, bias, nbr, num_out, taps, n_out, split, 0, out_feats,
+                                   stream_);
+}
+
+extern "C" int efgb_spconv_tc_forward_ex(const float* in_feats, int64_t num_in, int c_red, const float* packed,
+                                         const float* bias, const int32_t* nbr, int64_t num_out, int taps, int n_out,
+                                         int split, int relu, float* out_feats, efgb_stream_t stream_) {
   cudaStream_t stream = as_stream(stream_);
   EFGB_REQUIRE(tc::supported(c_red, n_out, taps), EFGB_EINVAL, "spconv_tc_forward: unsupported shape (c_red=%d n_out=%d taps=%d)",
                c_red, n_out, taps);
@@ -1038,6 +1056,7 @@ extern "C" int efgb_spconv_tc_forward(const float* in_feats, int64_t num_in, int
   p.in = in_feats;
   p.packed = packed;
   p.bias = bias;
+  p.relu = relu ? 1 : 0;
   p.nbr = nbr;
   p.out = out_feats;
   p.num_out = num_out;

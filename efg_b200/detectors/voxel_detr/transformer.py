@@ -57,9 +57,28 @@ class TransformerEncoderLayer(nn.Module):
 
     def forward(self, src, pos, src_shape, src_start_idx, ref_windows):
         attended = self.self_attn(_add_pos(src, pos), src, src_shape, None, src_start_idx, None, ref_windows)[0]
-        src = self.norm1(src + self.dropout1(attended))
+        src = self._add_norm(src, self.dropout1(attended), self.norm1)
+        rows = src.numel() // src.shape[-1]
+        if self._fast(src) and self.activation is F.relu and not (self.training and self.dropout.p > 0):
+            from ... import ops
+
+            if ops.fused_ffn_supported(rows, self.linear1.in_features, self.linear1.out_features, self.linear2.out_features):
+                ffn = ops.fused_ffn(src, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias)
+                return self._add_norm(src, self.dropout2(ffn), self.norm2)
         ffn = self.linear2(self.dropout(self.activation(self.linear1(src))))
-        return self.norm2(src + self.dropout2(ffn))
+        return self._add_norm(src, self.dropout2(ffn), self.norm2)
+
+    def _fast(self, t):
+        return getattr(self.linear1, "_tc", False) and t.is_cuda and t.dtype == torch.float32
+
+    def _add_norm(self, x, r, norm):
+        """norm(x + r): one fused kernel each way on the CUDA backend (csrc/layernorm.cu), else the reference's two ops."""
+        if self._fast(x) and norm.elementwise_affine and norm.bias is not None:
+            from ... import ops
+
+            if ops.add_layer_norm_supported(x.numel() // x.shape[-1], x.shape[-1]):
+                return ops.add_layer_norm(x, r, norm.weight, norm.bias, norm.eps)
+        return norm(x + r)
 
 
 class TransformerEncoder(nn.Module):

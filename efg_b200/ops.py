@@ -279,9 +279,10 @@ def spconv_tc_supported(c_red, n_out, taps):
     return CONV_PRECISION != "simt" and c_red >= 16 and bool(_lib.lib().efgb_spconv_tc_supported(c_red, n_out, taps))
 
 
-def spconv_tc(feats, w_param, bias, nbr, mode):
+def spconv_tc(feats, w_param, bias, nbr, mode, relu=False):
     """Tensor-core gather-GEMM.  w_param [c_out, taps, c_in] (reference layout), mode 0 fwd / 1 dgrad /
-    2 dgrad-submanifold; feats [Mi, c_red]; returns [nbr.shape[0], N]."""
+    2 dgrad-submanifold; feats [Mi, c_red]; returns [nbr.shape[0], N].  Fused epilogue: relu=True applies
+    max(x, 0) after the bias."""
     _check(feats, "features", torch.float32)
     _check(w_param, "weight", torch.float32)
     c_out, taps, c_in = w_param.shape
@@ -307,8 +308,8 @@ def spconv_tc(feats, w_param, bias, nbr, mode):
         t0 = PROFILER.begin()
     if bias is not None:
         _check(bias, "bias", torch.float32)
-    rc = L.efgb_spconv_tc_forward(_p(feats), feats.shape[0], c_red, _p(packed), _p(bias), _p(nbr), m_out, taps, n_out,
-                                  split, _p(out), _stream())
+    rc = L.efgb_spconv_tc_forward_ex(_p(feats), feats.shape[0], c_red, _p(packed), _p(bias), _p(nbr), m_out, taps, n_out,
+                                     split, 1 if relu else 0, _p(out), _stream())
     _lib.check(rc, "spconv_tc_forward")
     if t0 is not None:
         nbytes = 4 * (feats.shape[0] * c_red + m_out * n_out + taps * c_red * n_out + (taps * m_out if nbr is not None else 0))
@@ -421,6 +422,96 @@ class _DenseLinearFn(torch.autograd.Function):
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum(grad_out) if grad_out.shape[1] % 4 == 0 else grad_out.sum(0)
         return dx, dw, db
+
+
+class _FusedFFNFn(torch.autograd.Function):
+    """y = relu(x @ W1^T + b1) @ W2^T + b2 — the encoder FFN (VD/transformer.py:63: linear2(dropout(relu(linear1(src))))
+    with dropout = 0) on the tensor-core kernels with ReLU fused into the first GEMM's epilogue: the
+    [rows, dim_feedforward] pre-activation never exists in HBM."""
+
+    @staticmethod
+    def forward(ctx, x2d, w1, b1, w2, b2):
+        x2d = x2d.contiguous()
+        w1_3 = w1.contiguous().view(w1.shape[0], 1, w1.shape[1])
+        w2_3 = w2.contiguous().view(w2.shape[0], 1, w2.shape[1])
+        h = spconv_tc(x2d, w1_3, b1, None, 0, relu=True)
+        y = spconv_tc(h, w2_3, b2, None, 0)
+        ctx.save_for_backward(x2d, h, w1_3, w2_3)
+        ctx.has_bias = (b1 is not None, b2 is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2d, h, w1_3, w2_3 = ctx.saved_tensors
+        gy = gy.contiguous()
+        d_ff, _, d_in = w1_3.shape
+        d_out = w2_3.shape[0]
+        gh = torch.ops.aten.threshold_backward(spconv_tc(gy, w2_3, None, None, 1), h, 0)  # (gy @ W2) * (h > 0)
+        dw2 = spconv_tc_wgrad(h, gy, None, 1, d_ff, d_out).view(d_out, d_ff) if ctx.needs_input_grad[3] else None
+        db2 = colsum(gy) if ctx.has_bias[1] and ctx.needs_input_grad[4] else None
+        dx = spconv_tc(gh, w1_3, None, None, 1) if ctx.needs_input_grad[0] else None
+        dw1 = spconv_tc_wgrad(x2d, gh, None, 1, d_in, d_ff).view(d_ff, d_in) if ctx.needs_input_grad[1] else None
+        db1 = colsum(gh) if ctx.has_bias[0] and ctx.needs_input_grad[2] else None
+        return dx, dw1, db1, dw2, db2
+
+
+def fused_ffn_supported(rows, d_in, d_ff, d_out):
+    return (dense_linear_supported(rows, d_in, d_ff) and dense_linear_supported(rows, d_ff, d_out) and
+            d_ff % 4 == 0 and d_out % 4 == 0)
+
+
+def fused_ffn(x, w1, b1, w2, b2):
+    lead = x.shape[:-1]
+    y = _FusedFFNFn.apply(x.reshape(-1, x.shape[-1]), w1, b1, w2, b2)
+    return y.view(*lead, w2.shape[0])
+
+
+class _AddLayerNormFn(torch.autograd.Function):
+    """y = LayerNorm(x + residual) in one pass each way (csrc/layernorm.cu)."""
+
+    @staticmethod
+    def forward(ctx, x2d, r2d, weight, bias, eps):
+        x2d, r2d = x2d.contiguous(), r2d.contiguous()
+        weight, bias = weight.contiguous(), bias.contiguous()
+        for t, n in ((x2d, "x"), (r2d, "residual"), (weight, "weight"), (bias, "bias")):
+            _check(t, n, torch.float32)
+        rows, cols = x2d.shape
+        y = torch.empty_like(x2d)
+        z = torch.empty_like(x2d)
+        stats = torch.empty((2, rows), dtype=torch.float32, device=x2d.device)
+        t0 = PROFILER.begin() if PROFILER is not None else None
+        _lib.check(_lib.lib().efgb_add_layernorm_forward(_p(x2d), _p(r2d), _p(weight), _p(bias), rows, cols, float(eps), _p(y),
+                                                         _p(z), _p(stats[0]), _p(stats[1]), _stream()), "add_layernorm_forward")
+        if t0 is not None:
+            PROFILER.end("add_layernorm_fwd", t0, 4 * 4 * x2d.numel())
+        ctx.save_for_backward(z, stats, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        z, stats, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        rows, cols = z.shape
+        dz = torch.empty_like(z)
+        dgb = torch.empty((2, cols), dtype=torch.float32, device=z.device)
+        L = _lib.lib()
+        ws = workspace(L.efgb_add_layernorm_workspace_bytes(rows, cols), z.device)
+        t0 = PROFILER.begin() if PROFILER is not None else None
+        _lib.check(L.efgb_add_layernorm_backward(_p(dy), _p(z), _p(stats[0]), _p(stats[1]), _p(weight), rows, cols, _p(dz),
+                                                 _p(dgb[0]), _p(dgb[1]), _p(ws), ws.numel(), _stream()), "add_layernorm_backward")
+        if t0 is not None:
+            PROFILER.end("add_layernorm_bwd", t0, 3 * 4 * z.numel())
+        return dz, dz, dgb[0], dgb[1], None
+
+
+def add_layer_norm_supported(rows, cols):
+    return rows >= 4096 and bool(_lib.lib().efgb_add_layernorm_supported(cols))
+
+
+def add_layer_norm(x, residual, weight, bias, eps):
+    lead = x.shape
+    y = _AddLayerNormFn.apply(x.reshape(-1, x.shape[-1]), residual.reshape(-1, x.shape[-1]), weight, bias, eps)
+    return y.view(lead)
 
 
 def dense_linear_supported(rows, c_in, c_out):

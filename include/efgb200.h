@@ -168,6 +168,12 @@ int efgb_spconv_tc_forward(const float* in_feats, int64_t num_in, int c_red, con
                            const float* bias /* nullable [n_out] */, const int32_t* nbr,
                            int64_t num_out, int taps, int n_out, int split, float* out_feats,
                            efgb_stream_t stream);
+/* Same, with a fused epilogue: relu != 0 applies max(x, 0) after the bias (F.relu of the FFN,
+ * VD/transformer.py:63).  (Fusing ReLU's backward mask into the dgrad epilogue was measured and dropped: the
+ * per-row mask reads made the epilogue as long as the MMA phase.) */
+int efgb_spconv_tc_forward_ex(const float* in_feats, int64_t num_in, int c_red, const float* packed,
+                              const float* bias, const int32_t* nbr, int64_t num_out, int taps, int n_out,
+                              int split, int relu, float* out_feats, efgb_stream_t stream);
 
 /* Tensor-core wgrad: dw_param[co, tap, ci] = sum_o in[nbr[o,tap], ci] * grad_out[o, co], written in the
  * reference parameter layout [c_out, taps, c_in] (zero-filled by the callee, accumulated with
@@ -203,6 +209,24 @@ int efgb_dense_to_sparse(const float* dense, const int32_t* coords, int64_t num_
 int efgb_lsa_batched(const void* const* cost_ptrs_host, const int32_t* rows_host,
                      const int32_t* cols_host, const int32_t* ld_host, const int64_t* out_offsets_host,
                      int count, int64_t* out_rows, int64_t* out_cols, efgb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused residual add + LayerNorm over the last dimension (nn.LayerNorm(d_model) applied to
+ * src + dropout(x) in every encoder layer, VD/transformer.py:60-64), forward and backward.
+ *   forward:  z = x + residual (residual nullable); y = (z - mean) * rstd * gamma + beta; also writes z (nullable),
+ *             mean [rows], rstd [rows] for the backward.  rstd = 1/sqrt(biased var + eps), as torch.
+ *   backward: dz (= grad of x = grad of residual), dgamma, dbeta (deterministic two-pass column sums).
+ * cols % 128 == 0, 128 <= cols <= 512.  workspace: efgb_add_layernorm_workspace_bytes(rows, cols).
+ * ------------------------------------------------------------------------------------------ */
+int efgb_add_layernorm_supported(int cols);
+size_t efgb_add_layernorm_workspace_bytes(int64_t rows, int cols);
+int efgb_add_layernorm_forward(const float* x, const float* residual, const float* gamma,
+                               const float* beta, int64_t rows, int cols, float eps, float* y, float* z,
+                               float* mean, float* rstd, efgb_stream_t stream);
+int efgb_add_layernorm_backward(const float* dy, const float* z, const float* mean, const float* rstd,
+                                const float* gamma, int64_t rows, int cols, float* dz, float* dgamma,
+                                float* dbeta, void* workspace, size_t workspace_bytes,
+                                efgb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Column sums out[c] = sum_r x[r, c] of a row-major [rows, cols] f32 matrix (cols % 4 == 0): the bias
