@@ -309,7 +309,11 @@ def run_efgb200(args):
     ops.PROFILER = None
     prof_ms = t_prof0.elapsed_time(t_prof1) / prof_steps
 
+    if world > 1:
+        dist.barrier()
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     peaks = measured_peaks()
     kernels = {}
@@ -369,6 +373,8 @@ def run_efgb200(args):
     if not args.no_cpu_baseline and world >= 1:
         out["cpu_baseline"] = cpu_baseline(args, steps=1)
     print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # -------------------------------------------------------------------------------------------------

@@ -158,12 +158,15 @@ class Det3DLoss(nn.Module):
 
     @staticmethod
     def normaliser(targets, device):
-        """Mean number of GT boxes per rank, >= 1 (VD/losses.py:121-125); host value without a device sync
-        unless the job is distributed."""
+        """Mean number of GT boxes per rank, >= 1 (VD/losses.py:121-125): a host float in a single process, a 0-dim
+        device tensor (no host synchronisation) when the job is distributed over GPUs."""
         n = float(sum(len(t["labels"]) for t in targets))
         if _world_size() > 1:
             t = torch.as_tensor([n], dtype=torch.float, device=device)
             dist.all_reduce(t)
+            if t.is_cuda:
+                # stay on the device: a .item() here would drain the pipeline once per step on every rank
+                return (t / _world_size()).clamp_(min=1.0).reshape(())
             n = float(t.item())
         return max(n / _world_size(), 1.0)
 

@@ -50,30 +50,23 @@ class GradAverager:
         if self.world == 1:
             return 0
         grads = [p.grad for p in self.module.parameters() if p.grad is not None]
-        total, bucket, size = 0, [], 0
-        handles = []
-
-        def flush():
-            nonlocal bucket, size
-            if not bucket:
-                return
-            flat = torch.cat([g.reshape(-1) for g in bucket])
-            h = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)
-            handles.append((h, flat, bucket))
-            bucket, size = [], 0
-
+        buckets, bucket, size, total = [], [], 0, 0
         for g in grads:
             bucket.append(g)
             size += g.numel() * g.element_size()
             total += g.numel() * g.element_size()
             if size >= self.bucket_bytes:
-                flush()
-        flush()
+                buckets.append(bucket)
+                bucket, size = [], 0
+        if bucket:
+            buckets.append(bucket)
+        handles = []
+        for members in buckets:
+            flat = torch.cat([g.reshape(-1) for g in members])  # one batched copy kernel
+            handles.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True), flat, members))
         for h, flat, members in handles:
             h.wait()
             flat.div_(self.world)
-            off = 0
-            for g in members:
-                g.copy_(flat[off:off + g.numel()].view_as(g))
-                off += g.numel()
+            views = [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in members]), members)]
+            torch._foreach_copy_(members, views)  # multi-tensor copy back: a handful of launches, not one per gradient
         return total
