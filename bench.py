@@ -387,7 +387,9 @@ def cpu_step_fn(n_points, seed=1):
 
     torch.manual_seed(0)
     cfg = voxel_detr_config(model={"device": "cpu", "transformer": {"num_queries": NUM_QUERIES}})
-    model = VoxelDETR(cfg, backend=cpu_backend(), prune_unused=False).train()  # the reference evaluates every FPN level
+    model = VoxelDETR(cfg, backend=cpu_backend(), prune_unused=False).train()  # the reference evaluates every FPN level,
+    model.stacked_losses = False      # ... every decoder layer's loss separately,
+    model.reuse_proposal_head = False  # ... and the proposal head twice (VD/transformer.py:56, VD/voxel_detr.py:145)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, betas=(0.9, 0.99), eps=1e-9)
     scenes = make_scenes(1, n_points, seed=seed)
 

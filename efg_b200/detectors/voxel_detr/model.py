@@ -61,6 +61,7 @@ class VoxelDETR(nn.Module):
         self.config = config
         self.stacked_losses = True  # decoder-layer losses / matching costs evaluated on layer-stacked tensors
         self.device_matching = True  # Hungarian assignments on the GPU (no host round trip); False = host scipy
+        self.reuse_proposal_head = True  # False: evaluate the proposal head a second time for the loss, as the reference
 
         input_dim = len(config.dataset.format) if config.dataset.nsweeps == 1 else len(config.dataset.format) + 1
         self.input_dim = input_dim
@@ -218,7 +219,7 @@ class VoxelDETR(nn.Module):
         # the reference evaluates the proposal head twice on the same (memory, anchors) — once, detached, to pick the
         # top-k proposals (VD/transformer.py:56) and once for this loss (VD/voxel_detr.py:145); the transformer keeps
         # the first result, which is the same tensor with its graph attached
-        cached = getattr(self.transformer, "_enc_head_out", None)
+        cached = getattr(self.transformer, "_enc_head_out", None) if self.reuse_proposal_head else None
         enc_cls, enc_box = cached if cached is not None else prop(memory, anchors)
         self.transformer._enc_head_out = None
         bin_targets = TargetList(dict(t, labels=torch.zeros_like(t["labels"])) for t in targets)
