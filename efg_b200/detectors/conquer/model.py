@@ -12,7 +12,7 @@ import torch
 from torch import nn
 from torch.nn import functional as F
 
-from ..voxel_detr.losses import MatchIndex, TargetList, upload_matches
+from ..voxel_detr.losses import MatchIndex, TargetList, device_matches, upload_matches
 from ..voxel_detr.model import VoxelDETR
 from ..voxel_detr.transformer import Transformer
 from .cdn import dn_post_process, prepare_for_cdn
@@ -132,10 +132,14 @@ class ConQueR(VoxelDETR):
                    "aux_outputs": [{"pred_logits": a[:, :nq], "pred_boxes": b[:, :nq]}
                                    for a, b in zip(cls_out[:-1], box_out[:-1])]}
         mats = prop.losses.prepare(enc_out, bin_targets) + head.losses.prepare(dec_out, targets)
-        solved = head.losses.matcher.solve(mats)
-        bs = len(targets)
-        per_layer = [solved[i * bs:(i + 1) * bs] for i in range(len(solved) // max(bs, 1))]
-        matches = upload_matches(per_layer, targets.offsets, cls_out.device)
+        matcher = head.losses.matcher
+        if self.device_matching and mats and mats[0].is_cuda and "solve" not in matcher.__dict__:
+            matches = device_matches(mats, len(mats) // max(len(targets), 1), targets.offsets, cls_out.device)  # csrc/lsa.cu
+        else:
+            solved = matcher.solve(mats)
+            bs = len(targets)
+            per_layer = [solved[i * bs:(i + 1) * bs] for i in range(len(solved) // max(bs, 1))]
+            matches = upload_matches(per_layer, targets.offsets, cls_out.device)
         losses = {k + "_enc": v for k, v in prop.compute_losses(enc_out, bin_targets, num_boxes, solved=matches[:1]).items()}
         losses.update(head.compute_losses(dec_out, targets, num_boxes, solved=matches[1:]))
         if dn_meta is not None:

@@ -167,6 +167,45 @@ def test_conquer_train_losses_parity():
     assert torch.isfinite(gpu.projector[0].weight.grad).all()
 
 
+@pytest.mark.parametrize("family", ["voxel_detr", "conquer"])
+def test_device_matching_equals_host_scipy_matching(family):
+    """The same GPU model, same weights, same batch: Hungarian assignments solved on the device (csrc/lsa.cu) vs on
+    the host with scipy (the reference's path).  Identical assignments -> identical losses."""
+    from efg_b200.config import conquer_config
+    from efg_b200.detectors.conquer import ConQueR
+    from efg_b200.detectors.conquer.cdn import draw_noise
+    from test_model_cpu import SMALL
+
+    torch.manual_seed(0)
+    if family == "voxel_detr":
+        model = VoxelDETR(small_config("cuda", 40)).train()
+    else:
+        model = ConQueR(conquer_config(dataset={"pc_range": SMALL.pc_range, "voxel_size": SMALL.voxel_size, "max_voxel_num": 20000},
+                                       model={"device": "cuda", "transformer": {"num_queries": 40, "enc_layers": 1,
+                                                                                "dec_layers": 2}})).train()
+    scenes = small_batch(2, 6000, seed=41)
+    if family == "conquer":
+        total_gt = sum(len(a["labels"]) for _, a in scenes)
+        model.cdn_noise = draw_noise(2 * 3 * total_gt, 3, torch.device("cpu"), generator=torch.Generator().manual_seed(5))
+    # non-degenerate predictions (at initialisation all queries are nearly identical and the optimum is not unique)
+    with torch.no_grad():
+        for p in model.transformer.decoder.detection_head.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+    batch = [({"points": p}, {"annotations": a}) for p, a in scenes]
+    out = {}
+    import copy
+    gt_state = copy.deepcopy(model.transformer.decoder_gt.state_dict()) if family == "conquer" else None
+    for mode in (True, False):
+        model.device_matching = mode
+        if gt_state is not None:  # the EMA decoder moves at every training forward
+            model.transformer.decoder_gt.load_state_dict(gt_state)
+        torch.manual_seed(1)
+        out[mode] = {k: float(v) for k, v in model(batch).items()}
+    assert set(out[True]) == set(out[False])
+    for k in out[True]:
+        assert abs(out[True][k] - out[False][k]) <= 1e-5 * max(1.0, abs(out[False][k])), (k, out[True][k], out[False][k])
+
+
 def test_centerpoint_train_losses_parity():
     """CenterPoint (SpMiddleResNetFHD with biased SubM blocks, padding [0,1,1] stage, un-padded z-collapse)
     on the CUDA backend vs the CPU oracle backend: losses within 1e-3 relative, BEV features within 1e-3."""
