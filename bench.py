@@ -370,7 +370,7 @@ def run_efgb200(args):
         "kernels": kernels,
         "profiled_step_ms": round(prof_ms, 3),
     }
-    if not args.no_cpu_baseline and world >= 1:
+    if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only
         out["cpu_baseline"] = cpu_baseline(args, steps=1)
     print(json.dumps(out), flush=True)
     if world > 1:

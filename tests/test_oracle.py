@@ -159,3 +159,44 @@ def test_synthetic_scene_statistics():
     pairs = (nbr >= 0).sum() / len(coords)
     assert 5.3 < pairs < 8.1, pairs  # 6.7 +- 20%
     assert ann["gt_boxes"].shape[1] == 9 and ann["labels"].min() >= 1
+
+
+# --------------------------------------------------------------------------------------------------
+# linear sum assignment: the restatement (and the lane-parallel reduction order the CUDA kernel uses) vs scipy
+# --------------------------------------------------------------------------------------------------
+def _lsa_cases():
+    rng = np.random.default_rng(0)
+    for trial in range(90):
+        nr, nc = int(rng.integers(1, 45)), int(rng.integers(1, 45))
+        kind = trial % 3
+        if kind == 0:
+            yield rng.random((nr, nc)).astype(np.float32)
+        elif kind == 1:
+            yield rng.integers(0, 4, (nr, nc)).astype(np.float32)  # heavy ties
+        else:
+            yield np.round(rng.random((nr, nc)) * 3).astype(np.float32)
+    yield np.zeros((9, 5), np.float32)
+    yield np.ones((4, 11), np.float32)
+
+
+def test_lsa_restatement_equals_scipy_including_ties():
+    from scipy.optimize import linear_sum_assignment
+
+    from oracle import lsa
+
+    for c in _lsa_cases():
+        i0, j0 = linear_sum_assignment(c)
+        i1, j1 = lsa.lsa_sequential(c)
+        assert np.array_equal(i0, i1) and np.array_equal(j0, j1), c.shape
+
+
+def test_lsa_lane_parallel_reduction_order_equals_scipy():
+    from scipy.optimize import linear_sum_assignment
+
+    from oracle import lsa
+
+    for c in _lsa_cases():
+        i0, j0 = linear_sum_assignment(c)
+        for lanes in (32, 4):
+            i1, j1 = lsa.lsa_lane_parallel(c, lanes=lanes)
+            assert np.array_equal(i0, i1) and np.array_equal(j0, j1), (c.shape, lanes)
