@@ -46,9 +46,6 @@ def parse_args():
     ap.add_argument("--points", type=int, default=POINTS_PER_SCENE)
     ap.add_argument("--scenes", type=int, default=SCENES_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", action="store_true",
-                    help="experimental: replay the encoder fwd+bwd as CUDA graphs (capture currently fails with "
-                         "cudaErrorStreamCaptureImplicit in the backward graph; see DESIGN.md)")
     ap.add_argument("--cpu-points", type=int, default=POINTS_PER_SCENE)
     ap.add_argument("--profile-step", action="store_true",
                     help="for `ncu --profile-from-start off`: after the warm-up run ONE step between "
@@ -274,8 +271,6 @@ def run_efgb200(args):
 
     for i in range(max(args.warmup, 3)):
         step(resident[i % n_batches])
-        if i == 0 and args.graph:
-            model.capture_encoder_graph(args.scenes)  # encoder fwd+bwd as CUDA graph replays (static BEV shapes)
     barrier()
 
     if args.profile_step:
@@ -361,7 +356,7 @@ def run_efgb200(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "scenes_per_gpu": args.scenes, "points_per_scene": args.points,
                    "num_queries": NUM_QUERIES, "grid": "1504x1504x40", "step": "voxelize+fwd+bwd+allreduce+adamw",
-                   "cuda_graph": "encoder fwd+bwd" if args.graph else "none", "parallelism": "dp%d" % world, "l2": "flushed before every timed step (256 MiB memset, inside the timed span)"},
+                   "cuda_graph": "none", "parallelism": "dp%d" % world, "l2": "flushed before every timed step (256 MiB memset, inside the timed span)"},
         "e2e": {"value": round(e2e_value, 3), "unit": "scenes/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": last_loss},
         "gpu_launches": int(launches),

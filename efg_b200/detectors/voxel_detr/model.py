@@ -94,30 +94,6 @@ class VoxelDETR(nn.Module):
         self.grid_size = grid  # (x, y, z)
         self.to(self.device)
 
-    def capture_encoder_graph(self, batch_size):
-        """Replace the box-attention encoder by CUDA-graph replays of its forward and backward
-        (torch.cuda.make_graphed_callables).  The encoder is the launch-bound part of the step — ~1.5k small
-        kernels over tensors whose shapes depend only on the BEV geometry [B, H*W, C] — so one graph launch
-        replaces them; the sparse backbone (data-dependent row counts) and the loss (host matching) stay eager.
-        Call once, after a few eager warm-up steps with the same per-GPU batch size."""
-        tr = self.transformer
-        if getattr(tr, "_graphed", False) or self.device.type != "cuda":
-            return
-        stride = 8  # p3
-        h, w = int(self.grid_size[1]) // stride, int(self.grid_size[0]) // stride
-        dev = self.device
-        src = torch.randn(batch_size, h * w, self.hidden_dim, device=dev, requires_grad=True)
-        pos = torch.randn(batch_size, h * w, self.hidden_dim, device=dev)
-        feat = torch.zeros(batch_size, self.hidden_dim, h, w, device=dev)
-        anchors = tr._create_ref_windows([feat]).contiguous()
-        key = ("shapes", ((h, w),), dev)
-        if key not in tr._ref_cache:
-            shapes = torch.tensor([[h, w]], dtype=torch.int64, device=dev)
-            tr._ref_cache[key] = (shapes, torch.zeros(1, dtype=torch.int64, device=dev))
-        shapes, start = tr._ref_cache[key]
-        tr.encoder = torch.cuda.make_graphed_callables(tr.encoder, (src, pos, shapes, start, anchors))
-        tr._graphed = True
-
     def _build_transformer(self, config, t):
         return Transformer(d_model=t.hidden_dim, nhead=t.nhead, nlevel=len(config.model.backbone.out_features),
                            num_encoder_layers=t.enc_layers, num_decoder_layers=t.dec_layers,
