@@ -212,9 +212,10 @@ class Det3DLoss(nn.Module):
                 src_box, src_rad = src.split(6, dim=-1)
                 tgt_box, tgt_rad = tgt.split(6, dim=-1)
                 giou = generalized_box3d_iou_paired(cxcyczlwh_to_corners(src_box), cxcyczlwh_to_corners(tgt_box))
-                out["loss_bbox"] = F.l1_loss(src_box, tgt_box, reduction="none").view(L, -1).sum(1) / num_boxes
-                out["loss_giou"] = (1 - giou).view(L, -1).sum(1) / num_boxes
-                out["loss_rad"] = F.l1_loss(src_rad, tgt_rad, reduction="none").view(L, -1).sum(1) / num_boxes
+                # explicit sizes: n may be 0 (a batch without ground truth), where view(L, -1) is ambiguous
+                out["loss_bbox"] = F.l1_loss(src_box, tgt_box, reduction="none").view(L, n * src_box.shape[-1]).sum(1) / num_boxes
+                out["loss_giou"] = (1 - giou).view(L, n).sum(1) / num_boxes
+                out["loss_rad"] = F.l1_loss(src_rad, tgt_rad, reduction="none").view(L, n * src_rad.shape[-1]).sum(1) / num_boxes
         losses = {}
         for k, vec in out.items():
             for li in range(L):

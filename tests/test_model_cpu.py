@@ -210,3 +210,24 @@ def test_stacked_losses_equal_per_layer_reference_path():
     for n in g0:
         scale = max(1.0, g0[n].abs().max().item())
         assert (g0[n] - g1[n]).abs().max().item() <= 2e-4 * scale, n
+
+
+def test_losses_with_scenes_without_ground_truth():
+    """One scene of the batch (and then the whole batch) has no boxes: both loss evaluations must agree and stay
+    finite (the classification loss still sees every query as background)."""
+    torch.manual_seed(4)
+    cfg = small_config()
+    model = VoxelDETR(cfg, backend=cpu_backend()).train()
+    scenes = small_batch(2, 4000, seed=17)
+    empty = {k: v[:0] for k, v in scenes[1][1].items()}
+    for anns in ([scenes[0][1], empty], [empty, empty]):
+        batch = [(voxelized_sample(p, cfg.dataset), {"annotations": a}) for (p, _), a in zip(scenes, anns)]
+        res = []
+        for stacked in (False, True):
+            model.stacked_losses = stacked
+            losses = model(batch)
+            total = sum(v for k, v in losses.items() if k.startswith("loss"))
+            assert torch.isfinite(total)
+            res.append({k: float(v) for k, v in losses.items()})
+        for k in res[0]:
+            assert abs(res[0][k] - res[1][k]) <= 1e-5 * max(1.0, abs(res[0][k])), k
