@@ -65,6 +65,12 @@ def _compile_one(nvcc, src, deps, verbose, defines=(), tag=""):
 VARIANTS = {
     "pw8": ["-DEFGB_TC_PRODUCER_WARPS=8"],
     "pw16": ["-DEFGB_TC_PRODUCER_WARPS=16"],
+    "fmma": ["-DEFGB_TC_FENCE_AT_MMA=1"],
+    "abl1": ["-DEFGB_TC_ABLATE=1"],   # perf ablations of spconv_tc.cu (results invalid)
+    "abl2": ["-DEFGB_TC_ABLATE=2"],
+    "abl4": ["-DEFGB_TC_ABLATE=4"],
+    "abl6": ["-DEFGB_TC_ABLATE=6"],
+    "abl7": ["-DEFGB_TC_ABLATE=7"],
 }
 
 

@@ -3,24 +3,33 @@
 // Output-stationary implicit GEMM over the device rulebook:
 //     D[128 output rows x N] = sum over K = (tap, channel)  A[row, K] * B[n, K]
 //   A[row, (tap, c)] = in[nbr[row, tap], c]     gathered on the fly (zeros where nbr = -1)
-//   B[n,   (tap, c)] = weight element           pre-packed once per call into the exact shared-memory
-//                                               image (K-major, 128-byte swizzle) the tensor core reads
-// K is consumed in chunks of 32 floats = one 128-byte swizzled row per operand row.
+//   B[n,   (tap, c)] = weight element           pre-packed into the exact shared-memory image
+//                                               (K-major, 128-byte swizzle) the tensor core reads
+// K is consumed in chunks of one 128-byte swizzled row per operand row: 32 tf32 or 64 bf16 values.
 //
-// Roles inside one persistent CTA (one CTA per SM, tiles strided over the grid):
-//   (warp numbers for the default of 16 producer warps; measured 1.3x faster than 8 on the producer-bound layers)
-//   warps 0-15  A producers (four groups of 4 warps, each owning every 4th K chunk): 8 lanes gather one 128-byte
-//               row piece with coalesced LDG.128 (16 independent loads in flight per thread), split it
-//               into tf32 hi/lo parts, and store it swizzled into the stage's A tiles
-//   warp  16    MMA issuer: one elected lane issues tcgen05.mma.kind::tf32 (M=128, N, K=8) into TMEM;
+// Roles inside one persistent CTA (one CTA per SM, super-tiles strided over the grid):
+//   warps 0-15  A producers.  All 16 warps fill the SAME stage (a thread owns two 16-byte pieces of the
+//               128 x 128 B tile) and the loop is software-pipelined in registers: the gathers of stage s+1 and
+//               the rulebook entries of stage s+2 are in flight while stage s is converted and stored, so
+//               neither latency sits on the stage turnaround and a thread spends ~40 instructions per piece
+//               (round 1: four warp groups on four stages, one exposed latency per stage, ~70 instructions per
+//               piece — producers were issue- and latency-bound, profiles/r1_ncu_source_hotspots_spconv_tc.txt)
+//   warp  16    MMA issuer: one elected lane issues tcgen05.mma (M=128, N, 32 bytes of K) into TMEM;
 //               tcgen05.commit releases the stage / publishes the accumulator
-//   warp  17    B loader: one lane streams the packed weight chunk with cp.async.bulk (TMA engine,
-//               mbarrier complete_tx) — weights stay L2-resident
+//   warp  17    B loader: one lane streams the packed weight chunk with cp.async.bulk (bulk-copy engine,
+//               mbarrier complete_tx, no tensor map) — weights stay L2-resident
 //   warps 18-21 epilogue: tcgen05.ld the fp32 accumulator (double-buffered in TMEM), add bias, store rows
 //
-// Precision: kSplit = true runs the 3xTF32 scheme (a = a_hi + a_lo, b = b_hi + b_lo;
-// a_hi*b_hi + a_lo*b_hi + a_hi*b_lo with fp32 accumulation), error ~2^-21 relative, i.e. fp32-faithful
-// (the reference runs this path in fp32).  kSplit = false is single-pass TF32.
+// Precision modes (all accumulate in fp32 in TMEM):
+//   kBf16x3 (default)  a = a_hi + a_lo, b = b_hi + b_lo in bf16; a_hi*b_hi + a_hi*b_lo + a_lo*b_hi on kind::f16.
+//                      Error 2.5e-5 relative (scripts/numerics_split_precision.py), twice the MMA rate and half the
+//                      shared-memory operand bytes of 3xTF32.
+//   kTf32x3            the same three products with tf32 hi / lo parts (error ~2^-21, "fp32-faithful")
+//   kTf32              single pass
+// "Concatenated" issue (n_cta <= 128): [B_hi | B_lo] are adjacent in shared memory, so A_hi x [B_hi | B_lo]
+// is ONE MMA of N = 2 n_cta whose two column halves the epilogue adds; with A_lo x B_hi that is two reads of
+// the A tile per K step instead of three and 2/3 of the MMA instructions for the same tensor-pipe work.
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -29,7 +38,8 @@ namespace efgb {
 namespace tc {
 
 constexpr int kTileM = 128;
-constexpr int kChunkK = 32;             // floats per K chunk (128 bytes)
+constexpr int kChunkK = 32;             // tf32 values per K chunk (128 bytes)
+constexpr int kBf16ChunkK = 64;         // bf16 values per K chunk (128 bytes)
 #ifndef EFGB_TC_PRODUCER_WARPS
 #define EFGB_TC_PRODUCER_WARPS 16
 #endif
@@ -40,6 +50,26 @@ constexpr int kThreads = (kProducerWarps + 6) * 32;      // + MMA issuer, weight
 static_assert(kProducerWarps == 8 || kProducerWarps == 16, "producer warp groups assume 8 or 16 warps");
 static_assert((kProducerWarps + 2) % 4 == 2, "epilogue warps must cover the four TMEM lane quarters");
 constexpr int kMaxTaps = 32;
+
+enum : int { kTf32 = 0, kTf32x3 = 1, kBf16x3 = 2 };
+// Perf ablations for A/B library variants only (efg_b200/_build.py VARIANTS; results are invalid): 1 = MMAs skipped,
+// 2 = planes producers skip the copies, 4 = planes producers skip the rulebook loads.  The product build defines nothing.
+#ifndef EFGB_TC_ABLATE
+#define EFGB_TC_ABLATE 0
+#endif
+// Where the generic -> async proxy fence runs: 0 = in the producers (after their stores), 1 = in the MMA issuer (after its
+// acquire on the stage barrier).
+#ifndef EFGB_TC_FENCE_AT_MMA
+#define EFGB_TC_FENCE_AT_MMA 1
+#endif   // `split` argument of the C ABI
+
+template <int kMode>
+struct ModeTraits {
+  static constexpr int kParts = kMode == kTf32 ? 1 : 2;                    // operand images per stage (hi, lo)
+  static constexpr int kChunkVals = kMode == kBf16x3 ? kBf16ChunkK : kChunkK;  // K values per 128-byte row
+  static constexpr int kPieceVals = kChunkVals / 8;                        // K values per 16-byte shared-memory piece
+  static constexpr int kLoads = kPieceVals / 4;                            // LDG.128 per piece
+};
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -73,14 +103,24 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-// Ampere-style asynchronous 16-byte copy global -> shared; src_bytes = 0 writes zeros (missing neighbour).
+// Ampere-style asynchronous 16-byte copy global -> shared, L2 only; src_bytes = 0 writes zeros (missing neighbour).
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-// The mbarrier receives one arrival from this thread once all of its earlier cp.async copies have landed
-// (.noinc: the arrival is part of the barrier's initial count).
-__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+// One lane of a converged warp (elect.sync): the compiler keeps warp-uniform operands in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -96,6 +136,24 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+template <int kMode>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if constexpr ((EFGB_TC_ABLATE & 1) != 0) return;
+  if constexpr (kMode == kBf16x3)
+    tc_mma_bf16(tmem_d, adesc, bdesc, idesc, accum);
+  else
+    tc_mma_tf32(tmem_d, adesc, bdesc, idesc, accum);
 }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -120,15 +178,23 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// kind::tf32 instruction descriptor (mma_sm100_desc.hpp:InstrDescriptor): D=f32 [4,6)=1, A=tf32 [7,10)=2,
-// B=tf32 [10,13)=2, both K-major, N>>3 at [17,23), M>>4 at [24,29).
+// Instruction descriptor (mma_sm100_desc.hpp:InstrDescriptor): D=f32 [4,6)=1, A format [7,10), B format [10,13)
+// (kind::tf32: 2 = tf32; kind::f16: 1 = bf16), both K-major, N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+template <int kMode>
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return kMode == kBf16x3 ? make_idesc_bf16(m, n) : make_idesc_tf32(m, n);
 }
 
 struct Params {
   const float* in;       // [num_in, c_red]
-  const float* packed;   // [chunks][parts][n_out][32] swizzled image
+  const uint8_t* planes; // bf16x3 only, nullable: [num_in][hi | lo][c_red] bf16 — the input pre-split once (split_bf16_kernel)
+  const uint8_t* packed; // [chunks][parts][n_out][128 B] swizzled image
   const float* bias;     // [n_out] or null
   int relu;              // epilogue applies max(x, 0) after the bias
   const int32_t* nbr;    // [num_out, taps], or null = identity (dense GEMM: taps == 1, src row = out row)
@@ -137,21 +203,12 @@ struct Params {
   int c_red, taps, n_out, chunks;
   int num_tiles;         // 128-row tiles
   int n_cta;             // output columns per CTA (n_out / gridDim.y)
+  int acc_cols;          // TMEM columns of one tile accumulator: n_cta, or 2 n_cta with concatenated issue
+  int concat;            // 1: A_hi x [B_hi | B_lo] as one MMA of N = 2 n_cta (+ A_lo x B_hi); 0: three MMAs of N = n_cta
   int tiles_per_super;   // T: row tiles that share every weight chunk (accumulators side by side in TMEM)
   int num_super;         // ceil(num_tiles / T)
   int sa, sb;            // A-ring / B-ring depth
-  int async_gather;      // 1: cp.async producers (produce_a_async), 0: register-staged producers (produce_a)
   int cred_shift;        // log2(c_red) when c_red is a power of two, else -1
-  int debug;             // perf experiments only: 1 = no MMAs, 2 = no gather loads, 4 = no index loads,
-                         // 64 = async producers leave the raw fp32 words as the hi operand (relies on the tensor core
-                         // ignoring the 13 low mantissa bits)
-};
-
-template <bool kSplit>
-struct Smem {
-  static constexpr int kParts = kSplit ? 2 : 1;
-  static __host__ __device__ int a_bytes() { return kParts * kTileM * 128; }
-  static __host__ __device__ int b_bytes(int n) { return kParts * n * 128; }
 };
 
 // Work of one CTA: super-tiles st = blockIdx.x + i * gridDim.x; a super-tile is T consecutive 128-row tiles
@@ -172,234 +229,344 @@ struct CtaWork {
     total_a = n_super > 0 ? ((n_super - 1) * p.tiles_per_super + t_last) * p.chunks : 0;
   }
   __device__ __forceinline__ int tiles_in(const Params& p, int i) const { return i == n_super - 1 ? t_last : p.tiles_per_super; }
-  // A-stage index -> (tile, chunk)
-  __device__ __forceinline__ void locate(const Params& p, int ga, int* tile, int* chunk) const {
-    const int full = (n_super - 1) * p.chunks * p.tiles_per_super;
-    int i, c, t;
-    if (ga < full) {
-      const int per = p.chunks * p.tiles_per_super;
-      i = ga / per;
-      const int rem = ga - i * per;
-      c = rem / p.tiles_per_super;
-      t = rem - c * p.tiles_per_super;
-    } else {
-      const int rem = ga - full;
-      i = n_super - 1;
-      c = rem / t_last;
-      t = rem - c * t_last;
-    }
-    *tile = (static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x)) * p.tiles_per_super + t;
-    *chunk = c;
-  }
 };
 
-// A producers.  kGroups warp groups; group g owns every kGroups-th A stage of this CTA's stream, so kGroups
-// stages are gathered concurrently and every thread keeps 1024/(threads per group) independent 16-byte loads
-// in flight.  The rulebook entries of a group's NEXT stage are fetched while the gathers of the current one
-// are in flight, and the smem slot is only waited for after the loads were issued, so a stage costs one memory
-// latency.  kGroups must not exceed the A-ring depth (mbarrier parity would alias).
-template <bool kSplit, int kGroups>
-__device__ __forceinline__ void produce_a(const Params& p, const CtaWork& w, uint8_t* a_ring, uint64_t* a_full,
-                                          uint64_t* a_empty, const int warp, const int lane) {
-  constexpr int kWarpsPerGroup = kProducerWarps / kGroups;
-  constexpr int kPieces = (kTileM * 8) / (kWarpsPerGroup * 32);  // 16-byte pieces per thread per stage
-  const int a_part = kTileM * 128;
-  const int a_bytes = Smem<kSplit>::a_bytes();
-  const int gidx = warp / kWarpsPerGroup;
-  const int gw = warp % kWarpsPerGroup;
-  const int row_in_group = lane >> 3;  // 0..3
-  const int q = lane & 7;              // 16-byte piece of the 128-byte row
-
-  int32_t src_next[kPieces];
-  int tile_n = 0, chunk_n = 0;
-  auto load_indices = [&](int ga) {
-    w.locate(p, ga, &tile_n, &chunk_n);
-    const int64_t r0 = static_cast<int64_t>(tile_n) * kTileM;
-    const int kk = chunk_n * kChunkK + q * 4;
-    const int tap = kk / p.c_red;
-    const bool tap_ok = tap < p.taps;
-#pragma unroll
-    for (int i = 0; i < kPieces; ++i) {
-      const int64_t row = r0 + (i * kWarpsPerGroup + gw) * 4 + row_in_group;
-      int32_t v = -1;
-      if (tap_ok && row < p.num_out && !(p.debug & 4)) v = p.nbr ? __ldg(p.nbr + row * p.taps + tap) : static_cast<int32_t>(row);
-      src_next[i] = v;
-    }
-  };
-
-  int ga = gidx;
-  if (ga < w.total_a) load_indices(ga);
-  while (ga < w.total_a) {
-    const int kk = chunk_n * kChunkK + q * 4;
-    const int tap = kk / p.c_red;
-    const int ci = kk - tap * p.c_red;
-    float4 v[kPieces];
-#pragma unroll
-    for (int i = 0; i < kPieces; ++i) {
-      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (src_next[i] >= 0 && !(p.debug & 2))
-        v[i] = __ldg(reinterpret_cast<const float4*>(p.in + static_cast<int64_t>(src_next[i]) * p.c_red + ci));
-    }
-    const int round = ga / p.sa;
-    const int stage = ga - round * p.sa;
-    const uint32_t phase = static_cast<uint32_t>(round & 1);
-    const int ga_next = ga + kGroups;
-    if (ga_next < w.total_a) load_indices(ga_next);  // overlaps with the gathers above
-    mbar_wait(smem_u32(&a_empty[stage]), phase ^ 1);
-    uint8_t* a_hi = a_ring + static_cast<size_t>(stage) * a_bytes;
-    uint8_t* a_lo = a_hi + a_part;
-#pragma unroll
-    for (int i = 0; i < kPieces; ++i) {
-      if (p.debug & 8) break;
-      const int r = (i * kWarpsPerGroup + gw) * 4 + row_in_group;
-      const uint32_t off = static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(q ^ (r & 7)) << 4);
-      if (kSplit) {
-        float4 hi, lo;
-        hi.x = __uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u);
-        hi.y = __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u);
-        hi.z = __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u);
-        hi.w = __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u);
-        lo.x = v[i].x - hi.x;
-        lo.y = v[i].y - hi.y;
-        lo.z = v[i].z - hi.z;
-        lo.w = v[i].w - hi.w;
-        *reinterpret_cast<float4*>(a_hi + off) = hi;
-        *reinterpret_cast<float4*>(a_lo + off) = lo;
-      } else {
-        *reinterpret_cast<float4*>(a_hi + off) = v[i];
-      }
-    }
-    if (!(p.debug & 16)) fence_proxy_async();  // make the generic-proxy stores visible to the tensor core (async proxy)
-    __syncwarp();
-    if (lane == 0) mbar_arrive(smem_u32(&a_full[stage]));
-    ga = ga_next;
+// fp32 -> operand image conversion of one 4-value unit (one LDG.128 of a source row).
+//   kTf32:   the raw words (the tensor core ignores the 13 low mantissa bits)
+//   kTf32x3: hi = word & 0xFFFFE000, lo = v - hi (exact)                       16 bytes per image
+//   kBf16x3: hi = bf16_rn(v), lo = bf16_rn(v - hi)                              8 bytes per image
+template <int kMode>
+__device__ __forceinline__ void convert_store(uint8_t* a_hi, uint8_t* a_lo, uint32_t off, const float4& v) {
+  if constexpr (kMode == kTf32) {
+    *reinterpret_cast<float4*>(a_hi + off) = v;
+  } else if constexpr (kMode == kTf32x3) {
+    float4 hi, lo;
+    hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+    hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+    hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+    hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    lo.x = v.x - hi.x;
+    lo.y = v.y - hi.y;
+    lo.z = v.z - hi.z;
+    lo.w = v.w - hi.w;
+    *reinterpret_cast<float4*>(a_hi + off) = hi;
+    *reinterpret_cast<float4*>(a_lo + off) = lo;
+  } else {
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y);
+    const __nv_bfloat162 h23 = __floats2bfloat162_rn(v.z, v.w);
+    const uint32_t w01 = *reinterpret_cast<const uint32_t*>(&h01), w23 = *reinterpret_cast<const uint32_t*>(&h23);
+    const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - __uint_as_float(w01 << 16), v.y - __uint_as_float(w01 & 0xFFFF0000u));
+    const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - __uint_as_float(w23 << 16), v.w - __uint_as_float(w23 & 0xFFFF0000u));
+    *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(w01, w23);
+    *reinterpret_cast<uint2*>(a_lo + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
   }
 }
 
-// A producers, asynchronous variant.  All producer warps work on the SAME stage; a thread owns two 16-byte pieces
-// of the 128 x 128 B tile.  The gather itself is cp.async (LDGSTS): the row piece lands in its swizzled slot of the
-// stage without passing through registers, so `sa - 2` stages of gathers are in flight per CTA while the oldest
-// landed stage is split into tf32 hi / lo in place (LDS, 8 ALU ops, 2 STS per piece) — neither the rulebook
-// latency nor the gather latency sits on the critical path of a stage any more.
-//   a_empty[slot] (MMA commit)  ->  cp.async into slot, cp.async.mbarrier.arrive on raw_full[slot]
-//   raw_full[slot] (all copies landed)  ->  split in place, fence.proxy.async, a_full[slot]  ->  MMA
-template <bool kSplit>
-__device__ __forceinline__ void produce_a_async(const Params& p, const CtaWork& w, uint8_t* a_ring, uint64_t* a_full,
-                                                uint64_t* a_empty, uint64_t* raw_full, const int tid, const int lane) {
-  constexpr int kThreadsP = kProducerWarps * 32;
-  constexpr int kPieces = (kTileM * 8) / kThreadsP;    // 16-byte pieces per thread per stage
-  constexpr int kRowsPerPass = kThreadsP / 8;
+// A producers: see the role description at the top of the file.  Eight consecutive lanes own one row of the stage and
+// read it 128 contiguous bytes per request (lane l: the 4-value units l, l + 8, ... of the row's chunk), so a warp-wide
+// LDG.128 touches four 128-byte lines — the L1TEX wavefront count, which co-limited the round-1 producers with the
+// issue rate, is the minimum the gather allows.  A thread serves two rows (slot and slot + 64); its units have the
+// same tap / first channel in both rows.  Row slots are permuted inside a warp (0, 4, 1, 5 | 2, 6, 3, 7) so that the
+// two rows of a half-warp fall into different halves of the 128-byte swizzle: the 8-byte bf16 stores are conflict-free.
+template <int kMode>
+__device__ __forceinline__ void produce_a(const Params& p, const CtaWork& w, uint8_t* a_ring, uint64_t* a_full,
+                                          uint64_t* a_empty, const int tid, const int lane) {
+  using M = ModeTraits<kMode>;
+  static_assert(kProducerWarps == 16, "the row-slot mapping assumes 64 row slots of 8 lanes");
+  constexpr int kJ = M::kChunkVals / 32;      // units per row per thread (8 lanes x 4 values = 32 values per pass)
   const int a_part = kTileM * 128;
-  const int a_bytes = Smem<kSplit>::a_bytes();
-  const int q = tid & 7;            // 16-byte piece of the 128-byte row
-  const int r_base = tid >> 3;      // row of piece 0; piece i is row r_base + i * kRowsPerPass
-  uint32_t off[kPieces];
+  const int a_bytes = M::kParts * a_part;
+  const int l = tid & 7;
+  const int slot_id = tid >> 3;               // 0..63
+  const int wv = slot_id >> 2, jj = slot_id & 3;
+  const int r_lo = (wv >> 1) * 8 + (wv & 1) * 2 + (jj >> 1) + (jj & 1) * 4;   // row of this thread in the first 64 rows
+  uint32_t off[kJ];
 #pragma unroll
-  for (int i = 0; i < kPieces; ++i) {
-    const int r = r_base + i * kRowsPerPass;
-    off[i] = static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(q ^ (r & 7)) << 4);
+  for (int j = 0; j < kJ; ++j) {
+    const int u = l + 8 * j;
+    if constexpr (kMode == kBf16x3)
+      off[j] = static_cast<uint32_t>(r_lo) * 128u + (static_cast<uint32_t>((u >> 1) ^ (r_lo & 7)) << 4) + static_cast<uint32_t>(u & 1) * 8u;
+    else
+      off[j] = static_cast<uint32_t>(r_lo) * 128u + (static_cast<uint32_t>(u ^ (r_lo & 7)) << 4);
   }
   const int total = w.total_a;
   if (total == 0) return;
-  const int depth = p.sa - 2;       // stages of gathers in flight ahead of the one being split (host ensures sa >= 3)
+  const uint32_t c_red = static_cast<uint32_t>(p.c_red);
+  const bool one_tap = (p.c_red % M::kChunkVals) == 0;   // every unit of a chunk belongs to the same tap
 
-  // cursor over this CTA's stage stream (super-tile, chunk, tile-in-super-tile), advanced without divisions
-  int ci_s = 0, cc = 0, ct = 0, cti = w.tiles_in(p, 0);
-  int32_t src[kPieces];
-  int ci = 0;
-  auto load_idx = [&]() {
-    const int tile = (static_cast<int>(blockIdx.x) + ci_s * static_cast<int>(gridDim.x)) * p.tiles_per_super + ct;
-    const int64_t r0 = static_cast<int64_t>(tile) * kTileM;
-    const int kk = cc * kChunkK + q * 4;
-    const int tap = p.cred_shift >= 0 ? (kk >> p.cred_shift) : kk / p.c_red;
-    ci = kk - tap * p.c_red;
-    const bool tap_ok = tap < p.taps;
+  // cursor of the rulebook prefetch over this CTA's stage stream (super-tile, chunk, tile), no divisions
+  int cu_s = 0, cu_c = 0, cu_t = 0, cu_ti = w.tiles_in(p, 0);
+  auto load_idx = [&](int32_t (&src)[kJ][2], uint32_t (&ci)[kJ]) {
+    const int tile = (static_cast<int>(blockIdx.x) + cu_s * static_cast<int>(gridDim.x)) * p.tiles_per_super + cu_t;
+    const int row0 = tile * kTileM + r_lo;
+    const bool ok0 = row0 < p.num_out, ok1 = row0 + 64 < p.num_out;
+    const int32_t* n0 = p.nbr + static_cast<int64_t>(row0) * p.taps;
+    const int32_t* n1 = n0 + 64 * p.taps;
 #pragma unroll
-    for (int i = 0; i < kPieces; ++i) {
-      const int64_t row = r0 + r_base + i * kRowsPerPass;
-      int32_t v = -1;
-      if (tap_ok && row < p.num_out) v = p.nbr ? __ldg(p.nbr + row * p.taps + tap) : static_cast<int32_t>(row);
-      src[i] = v;
+    for (int j = 0; j < kJ; ++j) {
+      if (j > 0 && one_tap) {   // same rulebook entries as unit 0 (read from src[0] at gather time: no register copy of a pending load)
+        ci[j] = ci[0] + 32u * j;
+        continue;
+      }
+      const int kk = cu_c * M::kChunkVals + 4 * (l + 8 * j);
+      const int tap = p.cred_shift >= 0 ? (kk >> p.cred_shift) : kk / p.c_red;
+      ci[j] = static_cast<uint32_t>(kk - tap * p.c_red);
+      const bool tap_ok = tap < p.taps;
+      src[j][0] = (tap_ok && ok0) ? (p.nbr ? __ldg(n0 + tap) : row0) : -1;
+      src[j][1] = (tap_ok && ok1) ? (p.nbr ? __ldg(n1 + tap) : row0 + 64) : -1;
     }
-    if (++ct == cti) {  // advance the cursor
-      ct = 0;
-      if (++cc == p.chunks) {
-        cc = 0;
-        ++ci_s;
-        cti = w.tiles_in(p, ci_s);
+    if (++cu_t == cu_ti) {
+      cu_t = 0;
+      if (++cu_c == p.chunks) {
+        cu_c = 0;
+        ++cu_s;
+        cu_ti = w.tiles_in(p, cu_s);
       }
     }
   };
+  auto gather = [&](const int32_t (&src)[kJ][2], const uint32_t (&ci)[kJ], float4 (&v)[kJ][2]) {
+#pragma unroll
+    for (int j = 0; j < kJ; ++j) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        v[j][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // 32-bit element offset (the host checks num_in * c_red < 2^32)
+        const int32_t e = (j > 0 && one_tap) ? src[0][i] : src[j][i];
+        if (e >= 0)
+          v[j][i] = __ldg(reinterpret_cast<const float4*>(p.in + static_cast<size_t>(static_cast<uint32_t>(e) * c_red + ci[j])));
+      }
+    }
+  };
+  int slot = 0;
+  uint32_t phase = 0;
+  auto finish = [&](const float4 (&v)[kJ][2]) {
+    mbar_wait(smem_u32(&a_empty[slot]), phase ^ 1);
+    uint8_t* a_hi = a_ring + static_cast<size_t>(slot) * a_bytes;
+    uint8_t* a_lo = a_hi + a_part;
+#pragma unroll
+    for (int j = 0; j < kJ; ++j) {
+      convert_store<kMode>(a_hi, a_lo, off[j], v[j][0]);
+      convert_store<kMode>(a_hi, a_lo, off[j] + 64u * 128u, v[j][1]);
+    }
+    // No fence.proxy.async here: it lowers to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, and the MEMBAR waits for EVERY
+    // outstanding memory operation of the thread — including the gathers of the next stage, which serialised the
+    // software pipeline on one full memory latency per stage (measured: ~1600 cycles per stage whatever the producer
+    // did).  The stores are published by the release of mbarrier.arrive; the MMA issuer, which has no loads in
+    // flight, runs the proxy fence after its acquire on a_full.
+#if !EFGB_TC_FENCE_AT_MMA
+    fence_proxy_async();
+#endif
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&a_full[slot]));
+    if (++slot == p.sa) {
+      slot = 0;
+      phase ^= 1;
+    }
+  };
 
+  int32_t src_a[kJ][2], src_b[kJ][2];
+  uint32_t ci_a[kJ], ci_b[kJ];
+  float4 v_a[kJ][2], v_b[kJ][2];
+  load_idx(src_a, ci_a);
+  gather(src_a, ci_a, v_a);
+  if (total > 1) load_idx(src_b, ci_b);
+  for (int s = 0; s < total; s += 2) {
+    // stage s is in v_a; the rulebook entries of stage s+1 are in src_b
+    if (s + 1 < total) gather(src_b, ci_b, v_b);
+    if (s + 2 < total) load_idx(src_a, ci_a);
+    finish(v_a);
+    if (s + 1 < total) {
+      if (s + 2 < total) gather(src_a, ci_a, v_a);
+      if (s + 3 < total) load_idx(src_b, ci_b);
+      finish(v_b);
+    }
+  }
+}
+
+// A producers over a PRE-SPLIT input (bf16x3, sparse convolutions).  A gathered input row is used by ~14 output rows, so
+// splitting fp32 -> bf16 hi / lo inside the producers repeats the conversion 14 times and was what bound the kernel
+// (issue slots: ~90 instructions per 16-byte piece of the A tile, profiles/r2_ncu_spconv_regpath.txt).  Here the input has
+// been split once into `planes[row] = [hi c_red x bf16 | lo c_red x bf16]` (same bytes per row as fp32) and a piece of
+// the A tile is ONE cp.async (LDGSTS, zero-fill for a missing neighbour): no registers, no conversion, ~10 instructions
+// per piece, kDepth stages of gathers in flight per thread.
+//   per row and 64-value chunk the source bytes are, tap segment by tap segment, [hi run | lo run]; eight consecutive
+//   lanes copy 128 consecutive source bytes of one row (minimum number of L1TEX wavefronts), a thread serves rows
+//   r and r + 64 with two pieces each.
+constexpr int kPlaneDepth = 3;   // stages of cp.async in flight, odd (A ring depth must be >= kPlaneDepth + 2)
+static_assert(kPlaneDepth % 2 == 1, "the unrolled producer loop assumes an odd depth");
+
+__device__ __forceinline__ void produce_a_planes(const Params& p, const CtaWork& w, uint8_t* a_ring, uint64_t* a_full,
+                                                 uint64_t* a_empty, const int tid, const int lane) {
+  static_assert(kProducerWarps == 16, "the row-slot mapping assumes 64 row slots of 8 lanes");
+  const int a_part = kTileM * 128;
+  const int a_bytes = 2 * a_part;
+  const int total = w.total_a;
+  if (total == 0) return;
+  const int C = p.c_red;
+  const int seg_vals = C < kBf16ChunkK ? C : kBf16ChunkK;     // values of one tap inside a chunk
+  const int wp = seg_vals / 8;                                  // 16-byte pieces of a hi (or lo) run: 2, 4 or 8
+  const int tpc = kBf16ChunkK / seg_vals;                       // taps per chunk: 4, 2 or 1
+  const int j = tid & 7;
+  const int slot_id = tid >> 3;                                 // 0..63
+  const int r_lo = slot_id;                                     // rows r_lo and r_lo + 64
+  // per-thread constants of its two pieces (k = 0, 1): tap segment, hi/lo, shared-memory offset, source byte offset
+  int seg[2];
+  uint32_t dst_off[2], src_off[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int g = k * 8 + j;
+    seg[k] = g / (2 * wp);
+    const int within = g - seg[k] * 2 * wp;
+    const int is_lo = within >= wp ? 1 : 0;
+    const int piece = within - is_lo * wp;
+    const int q = seg[k] * wp + piece;                           // 16-byte piece of the 128-byte tile row
+    dst_off[k] = static_cast<uint32_t>(is_lo * a_part + r_lo * 128 + ((q ^ (r_lo & 7)) << 4));
+    src_off[k] = static_cast<uint32_t>(is_lo * C * 2 + piece * 16);
+  }
+  const bool two_taps = seg[1] != seg[0];
+  const uint32_t row_bytes = static_cast<uint32_t>(C) * 4u;
+  const uint32_t a_base = smem_u32(a_ring);
+
+  // stage cursor (super-tile, chunk, tile) of the rulebook prefetch, which runs two stages ahead of the copies:
+  // the entries are consumed a full stage time after their loads were issued, and never copied between registers
+  // (a register move of a pending load stalls on its latency: that was 22 % of all stall samples).
+  int cu_s = 0, cu_c = 0, cu_t = 0, cu_ti = w.tiles_in(p, 0);
+  struct Idx {
+    int32_t v[2][2];      // [piece k][row i]; v[1] is unused when both pieces belong to the same tap
+    uint32_t ci_bytes;    // byte offset of the chunk inside a tap's hi run (c_red > 64)
+  };
+  const int num_out = static_cast<int>(p.num_out);
+  auto load_idx = [&](Idx& x) {
+    const int tile = (static_cast<int>(blockIdx.x) + cu_s * static_cast<int>(gridDim.x)) * p.tiles_per_super + cu_t;
+    const int row0 = tile * kTileM + r_lo;
+    int tap0;
+    if (C <= kBf16ChunkK) {
+      tap0 = cu_c * tpc;
+      x.ci_bytes = 0;
+    } else {
+      const int kk = cu_c * kBf16ChunkK;
+      tap0 = p.cred_shift >= 0 ? (kk >> p.cred_shift) : kk / C;
+      x.ci_bytes = static_cast<uint32_t>(kk - tap0 * C) * 2u;
+    }
+    const uint32_t e0 = static_cast<uint32_t>(row0) * static_cast<uint32_t>(p.taps);
+    const uint32_t e1 = e0 + 64u * static_cast<uint32_t>(p.taps);
+    const bool ok0 = row0 < num_out, ok1 = row0 + 64 < num_out;
+    {
+      const int tap = tap0 + seg[0];
+      const bool tap_ok = tap < p.taps;
+      if constexpr ((EFGB_TC_ABLATE & 4) != 0) {
+        x.v[0][0] = (tap_ok && ok0) ? row0 : -1;
+        x.v[0][1] = (tap_ok && ok1) ? row0 + 64 : -1;
+      } else {
+      x.v[0][0] = (tap_ok && ok0) ? __ldg(p.nbr + (e0 + tap)) : -1;
+      x.v[0][1] = (tap_ok && ok1) ? __ldg(p.nbr + (e1 + tap)) : -1;
+      }
+    }
+    if (two_taps && (EFGB_TC_ABLATE & 4) == 0) {
+      const int tap = tap0 + seg[1];
+      const bool tap_ok = tap < p.taps;
+      x.v[1][0] = (tap_ok && ok0) ? __ldg(p.nbr + (e0 + tap)) : -1;
+      x.v[1][1] = (tap_ok && ok1) ? __ldg(p.nbr + (e1 + tap)) : -1;
+    }
+    if (++cu_t == cu_ti) {
+      cu_t = 0;
+      if (++cu_c == p.chunks) {
+        cu_c = 0;
+        ++cu_s;
+        cu_ti = w.tiles_in(p, cu_s);
+      }
+    }
+  };
   int islot = 0;
   uint32_t iphase = 0;
-  int issued = 0;
-  auto issue = [&]() {  // gather stage `issued` with the indices loaded by the previous call
+  auto issue = [&](const Idx& x) {   // copies of the stage whose rulebook entries are in x
     mbar_wait(smem_u32(&a_empty[islot]), iphase ^ 1);
-    const uint32_t dst = smem_u32(a_ring + static_cast<size_t>(islot) * a_bytes);
+    const uint32_t dst = a_base + static_cast<uint32_t>(islot) * static_cast<uint32_t>(a_bytes);
 #pragma unroll
-    for (int i = 0; i < kPieces; ++i) {
-      const bool ok = src[i] >= 0;
-      const float* g = ok ? p.in + static_cast<int64_t>(src[i]) * p.c_red + ci : p.in;
-      cp_async_16(dst + off[i], g, ok ? 16u : 0u);
+    for (int k = 0; k < 2; ++k) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int32_t e = (k == 1 && two_taps) ? x.v[1][i] : x.v[0][i];
+        const uint32_t row = static_cast<uint32_t>(e < 0 ? 0 : e);   // a valid address even when nothing is read
+        const uint8_t* g = p.planes + (static_cast<size_t>(row) * row_bytes + (src_off[k] + x.ci_bytes));
+        if constexpr ((EFGB_TC_ABLATE & 2) == 0) cp_async_16(dst + dst_off[k] + static_cast<uint32_t>(i * 64 * 128), g, e < 0 ? 0u : 16u);
+      }
     }
-    cp_async_mbar_arrive_noinc(smem_u32(&raw_full[islot]));
     if (++islot == p.sa) {
       islot = 0;
       iphase ^= 1;
     }
-    if (++issued < total) load_idx();  // consumed by the next issue(); its latency hides behind the split below
+  };
+  int cslot = 0;
+  auto complete = [&]() {
+    cp_async_commit();                   // possibly empty: one group per stage keeps the wait count constant
+    cp_async_wait<kPlaneDepth>();        // the copies of the oldest stage in flight have landed
+#if !EFGB_TC_FENCE_AT_MMA
+    fence_proxy_async();                 // -> visible to the tensor core (async proxy)
+#endif
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&a_full[cslot]));
+    if (++cslot == p.sa) cslot = 0;
   };
 
-  load_idx();
-  for (int t = 0; t < depth && t < total; ++t) issue();
-  int sslot = 0;
-  uint32_t sphase = 0;
-  for (int s = 0; s < total; ++s) {
-    if (issued < total) issue();
-    mbar_wait(smem_u32(&raw_full[sslot]), sphase);
-    uint8_t* a_hi = a_ring + static_cast<size_t>(sslot) * a_bytes;
-    uint8_t* a_lo = a_hi + a_part;
-    if (kSplit) {
-#pragma unroll
-      for (int i = 0; i < kPieces; ++i) {
-        const float4 v = *reinterpret_cast<const float4*>(a_hi + off[i]);
-        float4 hi, lo;
-        hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-        hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-        hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-        hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-        lo.x = v.x - hi.x;
-        lo.y = v.y - hi.y;
-        lo.z = v.z - hi.z;
-        lo.w = v.w - hi.w;
-        if (!(p.debug & 64)) *reinterpret_cast<float4*>(a_hi + off[i]) = hi;
-        *reinterpret_cast<float4*>(a_lo + off[i]) = lo;
+  // Stage n is issued from xa when n is even, from xb when n is odd; its entries were loaded two issues earlier.
+  Idx xa, xb;
+  load_idx(xa);
+  if (total > 1) load_idx(xb);
+  int n = 0;         // next stage to issue
+  int loaded = 2;    // stages whose rulebook entries have been requested
+  // prologue: kPlaneDepth stages in flight before the first completion (empty groups past the end)
+#pragma unroll 1
+  for (int d = 0; d < kPlaneDepth; ++d) {
+    if (n < total) {
+      if ((n & 1) == 0) {
+        issue(xa);
+        if (loaded < total) load_idx(xa);
+      } else {
+        issue(xb);
+        if (loaded < total) load_idx(xb);
       }
+      ++loaded;
+      ++n;
     }
-    fence_proxy_async();  // cp.async / st.shared writes -> visible to the tensor core (async proxy)
-    __syncwarp();
-    if (lane == 0) mbar_arrive(smem_u32(&a_full[sslot]));
-    if (++sslot == p.sa) {
-      sslot = 0;
-      sphase ^= 1;
+    cp_async_commit();
+  }
+  // steady state, unrolled by two so that xa / xb stay in fixed registers; kPlaneDepth is odd: stage n = s + 3
+#pragma unroll 1
+  for (int s = 0; s < total; s += 2) {
+    if (n < total) {           // n is odd here (kPlaneDepth odd, s even)
+      issue(xb);
+      if (loaded < total) load_idx(xb);
+      ++loaded;
+      ++n;
+    }
+    complete();
+    if (s + 1 < total) {
+      if (n < total) {
+        issue(xa);
+        if (loaded < total) load_idx(xa);
+        ++loaded;
+        ++n;
+      }
+      complete();
     }
   }
 }
 
-template <bool kSplit>
+template <int kMode>
 __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p) {
+  using M = ModeTraits<kMode>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the swizzle atoms
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  constexpr int kParts = Smem<kSplit>::kParts;
+  constexpr int kParts = M::kParts;
   const int n_cta = p.n_cta;  // output columns owned by this CTA (N split over grid.y)
   const int n0 = static_cast<int>(blockIdx.y) * n_cta;
   const int T = p.tiles_per_super;
-  const int a_bytes = Smem<kSplit>::a_bytes();
-  const int b_bytes = Smem<kSplit>::b_bytes(n_cta);
   const int a_part = kTileM * 128;
   const int b_part = n_cta * 128;
+  const int a_bytes = kParts * a_part;
+  const int b_bytes = kParts * b_part;
   uint8_t* a_ring = smem;
   uint8_t* b_ring = smem + static_cast<size_t>(p.sa) * a_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + static_cast<size_t>(p.sb) * b_bytes);
@@ -409,22 +576,19 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p) 
   uint64_t* b_empty = b_full + p.sb;
   uint64_t* tmem_full = b_empty + p.sb;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* raw_full = tmem_empty + 2;   // [sa], async producers only
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_full + p.sa);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int groups = p.sa >= 4 ? 4 : 2;  // producer warp groups (never more than A stages)
 
-  // TMEM: two sets of T accumulators of n_cta fp32 columns each, power of two >= 32
+  // TMEM: two sets of T accumulators of acc_cols fp32 columns each, power of two >= 32
   uint32_t tmem_cols = 32;
-  while (tmem_cols < static_cast<uint32_t>(2 * T * n_cta)) tmem_cols <<= 1;
+  while (tmem_cols < static_cast<uint32_t>(2 * T * p.acc_cols)) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.sa; ++s) {
-      mbar_init(smem_u32(&a_full[s]), p.async_gather ? kProducerWarps : kProducerWarps / groups);
+      mbar_init(smem_u32(&a_full[s]), kProducerWarps);
       mbar_init(smem_u32(&a_empty[s]), 1);
-      mbar_init(smem_u32(&raw_full[s]), kProducerWarps * 32);
     }
     for (int s = 0; s < p.sb; ++s) {
       mbar_init(smem_u32(&b_full[s]), 1);
@@ -449,18 +613,21 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p) 
 
   if (warp < kProducerWarps) {
     // ================= A producers =================
-    if (p.async_gather)
-      produce_a_async<kSplit>(p, w, a_ring, a_full, a_empty, raw_full, static_cast<int>(threadIdx.x), lane);
-    else if (groups == 4)
-      produce_a<kSplit, 4>(p, w, a_ring, a_full, a_empty, warp, lane);
-    else
-      produce_a<kSplit, 2>(p, w, a_ring, a_full, a_empty, warp, lane);
+    if constexpr (kMode == kBf16x3) {
+      if (p.planes)
+        produce_a_planes(p, w, a_ring, a_full, a_empty, static_cast<int>(threadIdx.x), lane);
+      else
+        produce_a<kMode>(p, w, a_ring, a_full, a_empty, static_cast<int>(threadIdx.x), lane);
+    } else {
+      produce_a<kMode>(p, w, a_ring, a_full, a_empty, static_cast<int>(threadIdx.x), lane);
+    }
   } else if (warp == kLoaderWarp) {
-    // ================= B loader: weight chunks through their own ring (TMA bulk copies) =================
+    // ================= B loader: weight chunks through their own ring (bulk copies) =================
     // A chunk serves all T tiles of the super-tile, and the ring runs ahead of the A stream, so neither the
-    // L2 latency nor the L2 bandwidth of the weights sits on the A-stage turnaround.
+    // L2 latency nor the L2 bandwidth of the weights sits on the A-stage turnaround.  The hi and lo slabs of the
+    // CTA's columns land next to each other: [B_hi | B_lo] is one 2 n_cta-row K-major tile for concatenated issue.
     if (lane == 0) {
-      const uint32_t part_bytes = static_cast<uint32_t>(n_cta) * 128u;
+      const uint32_t part_bytes = static_cast<uint32_t>(b_part);
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0; i < w.n_super; ++i) {
@@ -470,8 +637,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p) 
           mbar_arrive_expect_tx(bar, static_cast<uint32_t>(b_bytes));
           const uint32_t dst = smem_u32(b_ring + static_cast<size_t>(stage) * b_bytes);
           for (int part = 0; part < kParts; ++part) {
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.packed) +
-                                 (static_cast<size_t>(c * kParts + part) * p.n_out + n0) * 128u;
+            const uint8_t* src = p.packed + (static_cast<size_t>(c * kParts + part) * p.n_out + n0) * 128u;
             for (uint32_t o = 0; o < part_bytes; o += 16384u) {
               const uint32_t n = part_bytes - o < 16384u ? part_bytes - o : 16384u;
               bulk_g2s(dst + part * part_bytes + o, src + o, n, bar);
@@ -487,8 +653,16 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p) 
     __syncwarp();
   } else if (warp == kMmaWarp) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(kTileM, n_cta);
+    // The whole warp runs the loop convergently (waits included) and one elected lane issues: descriptors, TMEM
+    // addresses and barrier addresses then live in uniform registers.  (Round 1 ran the loop inside `if (lane == 0)`:
+    // in divergent code every tcgen05.mma operand went through R2UR moves, ~100 cycles per MMA — with the eight small-N
+    // MMAs of a C <= 64 stage that serial issue time, not shared memory, was what bound the kernel.)
+    {
+      const uint32_t idesc_n = make_idesc<kMode>(kTileM, n_cta);
+      const uint32_t idesc_2n = make_idesc<kMode>(kTileM, 2 * n_cta);
+      const uint32_t a_ring_u = smem_u32(a_ring), b_ring_u = smem_u32(b_ring);
+      const uint32_t a_full_u = smem_u32(a_full), a_empty_u = smem_u32(a_empty);
+      const uint32_t b_full_u = smem_u32(b_full), b_empty_u = smem_u32(b_empty);
       int sa_ = 0, sb_ = 0;
       uint32_t pa = 0, pb = 0;
       for (int i = 0; i < w.n_super; ++i) {
@@ -498,45 +672,57 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p) 
         mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
         tc_fence_after();
         for (int c = 0; c < p.chunks; ++c) {
-          mbar_wait(smem_u32(&b_full[sb_]), pb);
-          const uint32_t b_hi = smem_u32(b_ring + static_cast<size_t>(sb_) * b_bytes);
+          mbar_wait(b_full_u + sb_ * 8, pb);
+          const uint32_t b_hi = b_ring_u + static_cast<uint32_t>(sb_ * b_bytes);
           const uint64_t db_hi = make_desc_sw128(b_hi);
           const uint64_t db_lo = make_desc_sw128(b_hi + b_part);
           for (int t = 0; t < ti; ++t) {
-            mbar_wait(smem_u32(&a_full[sa_]), pa);
+            mbar_wait(a_full_u + sa_ * 8, pa);
+#if EFGB_TC_FENCE_AT_MMA
+            fence_proxy_async();   // the producers' generic-proxy writes (acquired above) -> visible to the async proxy
+#endif
             tc_fence_after();
-            const uint32_t a_hi = smem_u32(a_ring + static_cast<size_t>(sa_) * a_bytes);
+            const uint32_t a_hi = a_ring_u + static_cast<uint32_t>(sa_ * a_bytes);
             const uint64_t da_hi = make_desc_sw128(a_hi);
             const uint64_t da_lo = make_desc_sw128(a_hi + a_part);
-            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>((acc * T + t) * n_cta);
+            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>((acc * T + t) * p.acc_cols);
+            if (elect_one()) {
 #pragma unroll
-            for (int j = 0; j < kChunkK / 8; ++j) {
-              if (p.debug & 1) break;
-              const uint64_t adv = static_cast<uint64_t>(j * 2);  // 8 tf32 = 32 bytes = 2 x 16 B
-              if (kSplit) {
-                tc_mma_tf32(tmem_d, da_lo + adv, db_hi + adv, idesc, (c | j) ? 1u : 0u);
-                tc_mma_tf32(tmem_d, da_hi + adv, db_lo + adv, idesc, 1u);
-                tc_mma_tf32(tmem_d, da_hi + adv, db_hi + adv, idesc, 1u);
-              } else {
-                tc_mma_tf32(tmem_d, da_hi + adv, db_hi + adv, idesc, (c | j) ? 1u : 0u);
+              for (int j = 0; j < 4; ++j) {
+                const uint64_t adv = static_cast<uint64_t>(j * 2);  // 32 bytes of K = 2 x 16 B
+                const uint32_t accum = (c | j) ? 1u : 0u;
+                if constexpr (kParts == 2) {
+                  if (p.concat) {
+                    tc_mma<kMode>(tmem_d, da_hi + adv, db_hi + adv, idesc_2n, accum);   // [a_hi b_hi | a_hi b_lo]
+                    tc_mma<kMode>(tmem_d, da_lo + adv, db_hi + adv, idesc_n, 1u);       // first half += a_lo b_hi
+                  } else {
+                    tc_mma<kMode>(tmem_d, da_lo + adv, db_hi + adv, idesc_n, accum);
+                    tc_mma<kMode>(tmem_d, da_hi + adv, db_lo + adv, idesc_n, 1u);
+                    tc_mma<kMode>(tmem_d, da_hi + adv, db_hi + adv, idesc_n, 1u);
+                  }
+                } else {
+                  tc_mma<kMode>(tmem_d, da_hi + adv, db_hi + adv, idesc_n, accum);
+                }
               }
+              tc_commit(a_empty_u + sa_ * 8);  // A stage reusable once these MMAs have read it
             }
-            tc_commit(smem_u32(&a_empty[sa_]));  // A stage reusable once these MMAs have read it
+            __syncwarp();
             if (++sa_ == p.sa) {
               sa_ = 0;
               pa ^= 1;
             }
           }
-          tc_commit(smem_u32(&b_empty[sb_]));    // weight chunk consumed by all tiles of the super-tile
+          if (elect_one()) tc_commit(b_empty_u + sb_ * 8);    // weight chunk consumed by all tiles of the super-tile
+          __syncwarp();
           if (++sb_ == p.sb) {
             sb_ = 0;
             pb ^= 1;
           }
         }
-        tc_commit(smem_u32(&tmem_full[acc]));    // accumulators of the super-tile complete
+        if (elect_one()) tc_commit(smem_u32(&tmem_full[acc]));    // accumulators of the super-tile complete
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else {
     // ================= epilogue (4 warps; warp w may only touch TMEM lanes 32*(w%4)..+31) =================
     const int quarter = warp & 3;
@@ -548,12 +734,20 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p) 
       tc_fence_after();
       for (int t = 0; t < ti; ++t) {
         const int64_t row = (static_cast<int64_t>(st) * T + t) * kTileM + quarter * 32 + lane;
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>((acc * T + t) * n_cta);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>((acc * T + t) * p.acc_cols);
         for (int c0 = 0; c0 < n_cta; c0 += 16) {
           uint32_t r[16];
           tc_ld16(taddr + c0, r);
-          tc_wait_ld();
-          if (row < p.num_out && !(p.debug & 32)) {
+          if (p.concat) {
+            uint32_t r2[16];
+            tc_ld16(taddr + n_cta + c0, r2);
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+          } else {
+            tc_wait_ld();
+          }
+          if (row < p.num_out) {
             float* dst = p.out + row * p.n_out + n0 + c0;
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
@@ -626,6 +820,36 @@ pack_weights_kernel(const float* __restrict__ w, int c_out, int taps, int c_in, 
   }
 }
 
+
+// bf16x3 weight image: [chunk of 64 K-values][hi | lo][n][64 bf16], K-major, 128-byte swizzle (16-byte pieces of 8 values).
+__global__ void __launch_bounds__(256)
+pack_weights_bf16_kernel(const float* __restrict__ w, int c_out, int taps, int c_in, int mode, int n_out, int c_red, int chunks,
+                         __nv_bfloat16* __restrict__ packed) {
+  const int64_t total = static_cast<int64_t>(chunks) * n_out * kBf16ChunkK;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int kk = static_cast<int>(t % kBf16ChunkK);
+  const int n = static_cast<int>((t / kBf16ChunkK) % n_out);
+  const int chunk = static_cast<int>(t / (static_cast<int64_t>(kBf16ChunkK) * n_out));
+  const int kidx = chunk * kBf16ChunkK + kk;
+  const int tap = kidx / c_red;
+  const int c = kidx - tap * c_red;
+  float v = 0.f;
+  if (tap < taps) {
+    if (mode == 0) {
+      if (n < c_out) v = w[(static_cast<int64_t>(n) * taps + tap) * c_in + c];
+    } else {
+      const int st = mode == 2 ? taps - 1 - tap : tap;
+      if (n < c_in) v = w[(static_cast<int64_t>(c) * taps + st) * c_in + n];
+    }
+  }
+  const int qphys = (kk >> 3) ^ (n & 7);
+  const int64_t off = static_cast<int64_t>(n) * kBf16ChunkK + qphys * 8 + (kk & 7);
+  __nv_bfloat16* base = packed + static_cast<int64_t>(chunk) * 2 * n_out * kBf16ChunkK;
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  base[off] = hi;
+  base[static_cast<int64_t>(n_out) * kBf16ChunkK + off] = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
 
 // ================================================================================================
 // wgrad on the tensor cores:  dW[(tap, ci), co] = sum over output rows  A[row, (tap, ci)] * G[row, co]
@@ -983,6 +1207,20 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_wgrad_tc_kernel(const Wgra
   }
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) function attribute: remember per device
+// which of the kernels have been configured (a process may drive several GPUs).
+template <typename Kernel>
+static cudaError_t ensure_max_smem(Kernel kernel, int slot) {
+  static unsigned char done[64][8] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && done[dev][slot]) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev][slot] = 1;
+  return e;
+}
+
 static bool wgrad_supported(int c_in, int c_out, int taps) {
   const bool cin_ok = c_in >= 16 && c_in % 4 == 0 && ((128 % c_in == 0) || (c_in % 128 == 0));
   const bool cout_ok = c_out >= 16 && c_out % 16 == 0 && (c_out <= 256 || (c_out % 256 == 0 && c_out <= 4096));
@@ -995,6 +1233,34 @@ static bool supported(int c_red, int n_out, int taps) {
 }
 
 static int chunks_for(int taps, int c_red) { return (taps * c_red + kChunkK - 1) / kChunkK; }
+static int chunks_for_bf16(int taps, int c_red) { return (taps * c_red + kBf16ChunkK - 1) / kBf16ChunkK; }
+static bool supported_bf16(int c_red, int n_out, int taps) { return supported(c_red, n_out, taps) && c_red % 8 == 0; }
+static bool planes_supported(int c_red) { return c_red == 16 || c_red == 32 || (c_red >= 64 && c_red % 64 == 0); }
+
+// fp32 [rows, C] -> planes [rows][hi C x bf16 | lo C x bf16]: hi = bf16_rn(v), lo = bf16_rn(v - hi).  One thread per 8 values.
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ in, int64_t rows, int C, uint8_t* __restrict__ planes) {
+  const int upr = C / 8;
+  const int64_t units = rows * upr;
+  for (int64_t u = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; u < units; u += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = u / upr;
+    const int k = static_cast<int>(u - row * upr);
+    const float4* g = reinterpret_cast<const float4*>(in + row * C + k * 8);
+    const float4 a = __ldg(g), b = __ldg(g + 1);
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      const uint32_t hw = *reinterpret_cast<const uint32_t*>(&hh);
+      const __nv_bfloat162 ll = __floats2bfloat162_rn(f[2 * i] - __uint_as_float(hw << 16), f[2 * i + 1] - __uint_as_float(hw & 0xFFFF0000u));
+      hi[i] = hw;
+      lo[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    uint8_t* dst = planes + row * C * 4 + k * 16;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(dst + C * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
 
 }  // namespace tc
 }  // namespace efgb
@@ -1005,6 +1271,10 @@ extern "C" int efgb_spconv_tc_supported(int c_red, int n_out, int taps) { return
 
 extern "C" size_t efgb_spconv_tc_packed_bytes(int taps, int c_red, int n_out, int split) {
   if (!tc::supported(c_red, n_out, taps)) return 0;
+  if (split == 2) {  // bf16x3: chunks of 64 K-values, hi + lo, 2 bytes each
+    if (!tc::supported_bf16(c_red, n_out, taps)) return 0;
+    return static_cast<size_t>(tc::chunks_for_bf16(taps, c_red)) * 2 * n_out * tc::kBf16ChunkK * sizeof(__nv_bfloat16);
+  }
   return static_cast<size_t>(tc::chunks_for(taps, c_red)) * (split ? 2 : 1) * n_out * tc::kChunkK * sizeof(float);
 }
 
@@ -1016,6 +1286,15 @@ extern "C" int efgb_spconv_tc_pack(const float* w_param, int c_out, int taps, in
   const int c_red = mode == 0 ? c_in : c_out;
   EFGB_REQUIRE(tc::supported(c_red, n_out, taps), EFGB_EINVAL, "spconv_tc_pack: unsupported shape (c_red=%d n_out=%d taps=%d)",
                c_red, n_out, taps);
+  if (split == 2) {
+    EFGB_REQUIRE(tc::supported_bf16(c_red, n_out, taps), EFGB_EINVAL, "spconv_tc_pack: bf16x3 needs c_red %% 8 == 0 (c_red=%d)", c_red);
+    const int chunks16 = tc::chunks_for_bf16(taps, c_red);
+    const int64_t total16 = static_cast<int64_t>(chunks16) * n_out * tc::kBf16ChunkK;
+    tc::pack_weights_bf16_kernel<<<static_cast<unsigned>((total16 + 255) / 256), 256, 0, stream>>>(
+        w_param, c_out, taps, c_in, mode, n_out, c_red, chunks16, reinterpret_cast<__nv_bfloat16*>(packed));
+    EFGB_LAUNCH_OK("pack_weights_bf16_kernel");
+    return EFGB_OK;
+  }
   const int chunks = tc::chunks_for(taps, c_red);
   const int64_t total = static_cast<int64_t>(chunks) * n_out * tc::kChunkK;
   const unsigned nb = static_cast<unsigned>((total + 255) / 256);
@@ -1038,23 +1317,30 @@ extern "C" int efgb_spconv_tc_forward(const float* in_feats, int64_t num_in, int
                                    stream_);
 }
 
-extern "C" int efgb_spconv_tc_forward_ex(const float* in_feats, int64_t num_in, int c_red, const float* packed,
-                                         const float* bias, const int32_t* nbr, int64_t num_out, int taps, int n_out,
-                                         int split, int relu, float* out_feats, efgb_stream_t stream_) {
+static int launch_forward(const float* in_feats, const void* planes, int64_t num_in, int c_red, const float* packed,
+                          const float* bias, const int32_t* nbr, int64_t num_out, int taps, int n_out, int split, int relu,
+                          float* out_feats, efgb_stream_t stream_) {
   cudaStream_t stream = as_stream(stream_);
-  EFGB_REQUIRE(tc::supported(c_red, n_out, taps), EFGB_EINVAL, "spconv_tc_forward: unsupported shape (c_red=%d n_out=%d taps=%d)",
-               c_red, n_out, taps);
+  EFGB_REQUIRE(split >= 0 && split <= 2, EFGB_EINVAL, "spconv_tc_forward: split must be 0 (tf32), 1 (tf32x3) or 2 (bf16x3)");
+  EFGB_REQUIRE(tc::supported(c_red, n_out, taps) && (split != 2 || tc::supported_bf16(c_red, n_out, taps)), EFGB_EINVAL,
+               "spconv_tc_forward: unsupported shape (c_red=%d n_out=%d taps=%d split=%d)", c_red, n_out, taps, split);
   EFGB_REQUIRE(num_in >= 0 && num_out >= 0, EFGB_EINVAL, "spconv_tc_forward: bad sizes");
   EFGB_REQUIRE(nbr != nullptr || (taps == 1 && num_in >= num_out), EFGB_EINVAL,
                "spconv_tc_forward: a null rulebook means identity and needs taps == 1");
   if (num_out == 0) return EFGB_OK;
-  EFGB_REQUIRE(packed && out_feats && (in_feats || num_in == 0), EFGB_EINVAL, "spconv_tc_forward: null pointer");
+  EFGB_REQUIRE(packed && out_feats && (in_feats || planes || num_in == 0), EFGB_EINVAL, "spconv_tc_forward: null pointer");
+  EFGB_REQUIRE(planes == nullptr || (split == 2 && nbr != nullptr && tc::planes_supported(c_red) &&
+                                     (reinterpret_cast<uintptr_t>(planes) & 15) == 0),
+               EFGB_EINVAL, "spconv_tc_forward: pre-split planes need bf16x3, a rulebook and c_red in {16, 32, 64 k} (c_red=%d)", c_red);
   EFGB_REQUIRE((reinterpret_cast<uintptr_t>(in_feats) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_feats) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(packed) & 15) == 0,
                EFGB_EINVAL, "spconv_tc_forward: feature / weight pointers must be 16-byte aligned");
+  EFGB_REQUIRE(static_cast<uint64_t>(num_in) * static_cast<uint64_t>(c_red) < (1ull << 32) && num_out < (1ll << 31) - 256,
+               EFGB_EINVAL, "spconv_tc_forward: input larger than 2^32 elements (the producers use 32-bit element offsets)");
   tc::Params p;
   p.in = in_feats;
-  p.packed = packed;
+  p.planes = reinterpret_cast<const uint8_t*>(planes);
+  p.packed = reinterpret_cast<const uint8_t*>(packed);
   p.bias = bias;
   p.relu = relu ? 1 : 0;
   p.nbr = nbr;
@@ -1063,17 +1349,14 @@ extern "C" int efgb_spconv_tc_forward_ex(const float* in_feats, int64_t num_in, 
   p.c_red = c_red;
   p.taps = taps;
   p.n_out = n_out;
-  p.chunks = tc::chunks_for(taps, c_red);
+  p.chunks = split == 2 ? tc::chunks_for_bf16(taps, c_red) : tc::chunks_for(taps, c_red);
   p.num_tiles = static_cast<int>((num_out + tc::kTileM - 1) / tc::kTileM);
-  {
-    const char* dbg = getenv("EFGB_TC_DEBUG");
-    p.debug = dbg ? atoi(dbg) : 0;
-  }
   // N split: wide outputs (dense GEMMs) are cut into 256-column slabs over grid.y
   int n_split = n_out > 256 ? n_out / 256 : 1;
   int n_cta = n_out / n_split;
-  // super-tile: T row tiles share each weight chunk (T * n_cta fp32 columns per accumulator set, two sets)
-  int T = 256 / n_cta;
+  // super-tile: T row tiles share each weight chunk (T * acc_cols fp32 columns per accumulator set, two sets in TMEM)
+  auto acc_cols_of = [&](int n) { return (split != 0 && n <= 128) ? 2 * n : n; };
+  int T = 256 / acc_cols_of(n_cta);
   if (T > 8) T = 8;
   if (T < 1) T = 1;
   // keep at least ~3/4 of the SMs busy; beyond that, sharing weight chunks across more tiles wins (the weight
@@ -1087,6 +1370,8 @@ extern "C" int efgb_spconv_tc_forward_ex(const float* in_feats, int64_t num_in, 
     }
   }
   p.n_cta = n_cta;
+  p.acc_cols = acc_cols_of(n_cta);
+  p.concat = p.acc_cols != n_cta ? 1 : 0;
   p.tiles_per_super = T;
   p.num_super = (p.num_tiles + T - 1) / T;
   const int parts = split ? 2 : 1;
@@ -1097,39 +1382,63 @@ extern "C" int efgb_spconv_tc_forward_ex(const float* in_feats, int64_t num_in, 
   p.sa = (budget - p.sb * b_bytes) / a_bytes;
   if (p.sa > 6) p.sa = 6;
   EFGB_REQUIRE(p.sa >= 2, EFGB_EINVAL, "spconv_tc_forward: tile does not fit shared memory");
-  {
-    // EFGB_TC_PRODUCER=async selects the cp.async producers (need >= 3 A stages).  Measured on B200 they are ~20 %
-    // SLOWER than the register-staged ones on the sparse layers (96 vs 77 us at C=16, 184 vs 147 us at C=64) and equal
-    // on the dense ones: the stage rate is bound by shared-memory bandwidth (SS-mode tcgen05.mma re-reads A and B
-    // from shared memory for each of the three split products), and the in-place split adds a read + a write per piece.
-    const char* prod = getenv("EFGB_TC_PRODUCER");
-    p.async_gather = (p.sa >= 3 && prod && strcmp(prod, "async") == 0) ? 1 : 0;
-    p.cred_shift = -1;
-    for (int sft = 2; sft < 16; ++sft)
-      if ((1 << sft) == c_red) p.cred_shift = sft;
-  }
+  EFGB_REQUIRE(!planes || p.sa >= tc::kPlaneDepth + 2, EFGB_EINVAL, "spconv_tc_forward: A ring too shallow for the cp.async producers");
+  p.cred_shift = -1;
+  for (int sft = 2; sft < 16; ++sft)
+    if ((1 << sft) == c_red) p.cred_shift = sft;
   const size_t smem = 1024 + static_cast<size_t>(p.sa) * a_bytes + static_cast<size_t>(p.sb) * b_bytes +
-                      (3 * p.sa + 2 * p.sb + 4) * 8 + 16;
+                      (2 * p.sa + 2 * p.sb + 4) * 8 + 16;
   int gx = kNumSMs / n_split;
   if (gx < 1) gx = 1;
   if (gx > p.num_super) gx = p.num_super;
   const dim3 grid(gx, n_split);
-  if (split) {
-    static bool configured = false;
-    if (!configured) {
-      EFGB_CUDA_OK(cudaFuncSetAttribute(tc::spconv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      configured = true;
-    }
-    tc::spconv_tc_kernel<true><<<grid, tc::kThreads, smem, stream>>>(p);
+  if (split == 2) {
+    EFGB_CUDA_OK(tc::ensure_max_smem(tc::spconv_tc_kernel<tc::kBf16x3>, 0));
+    tc::spconv_tc_kernel<tc::kBf16x3><<<grid, tc::kThreads, smem, stream>>>(p);
+  } else if (split == 1) {
+    EFGB_CUDA_OK(tc::ensure_max_smem(tc::spconv_tc_kernel<tc::kTf32x3>, 1));
+    tc::spconv_tc_kernel<tc::kTf32x3><<<grid, tc::kThreads, smem, stream>>>(p);
   } else {
-    static bool configured = false;
-    if (!configured) {
-      EFGB_CUDA_OK(cudaFuncSetAttribute(tc::spconv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      configured = true;
-    }
-    tc::spconv_tc_kernel<false><<<grid, tc::kThreads, smem, stream>>>(p);
+    EFGB_CUDA_OK(tc::ensure_max_smem(tc::spconv_tc_kernel<tc::kTf32>, 2));
+    tc::spconv_tc_kernel<tc::kTf32><<<grid, tc::kThreads, smem, stream>>>(p);
   }
   EFGB_LAUNCH_OK("spconv_tc_kernel");
+  return EFGB_OK;
+}
+
+extern "C" int efgb_spconv_tc_forward_ex(const float* in_feats, int64_t num_in, int c_red, const float* packed,
+                                         const float* bias, const int32_t* nbr, int64_t num_out, int taps, int n_out,
+                                         int split, int relu, float* out_feats, efgb_stream_t stream_) {
+  return launch_forward(in_feats, nullptr, num_in, c_red, packed, bias, nbr, num_out, taps, n_out, split, relu, out_feats, stream_);
+}
+
+extern "C" int efgb_spconv_tc_planes_supported(int c_red, int n_out, int taps) {
+  if (!tc::supported_bf16(c_red, n_out, taps) || !tc::planes_supported(c_red)) return 0;
+  // the cp.async producers need kPlaneDepth + 2 A stages next to the weight ring
+  const int n_cta = n_out > 256 ? 256 : n_out;
+  const int b_bytes = 2 * n_cta * 128;
+  const int sb = b_bytes >= 65536 ? 2 : (b_bytes >= 16384 ? 3 : 4);
+  return (227 * 1024 - 2048 - sb * b_bytes) / (2 * tc::kTileM * 128) >= tc::kPlaneDepth + 2 ? 1 : 0;
+}
+
+extern "C" int efgb_spconv_tc_forward_planes(const void* in_planes, int64_t num_in, int c_red, const float* packed,
+                                             const float* bias, const int32_t* nbr, int64_t num_out, int taps, int n_out,
+                                             int relu, float* out_feats, efgb_stream_t stream_) {
+  EFGB_REQUIRE(in_planes || num_in == 0 || num_out == 0, EFGB_EINVAL, "spconv_tc_forward_planes: null input");
+  EFGB_REQUIRE(efgb_spconv_tc_planes_supported(c_red, n_out, taps), EFGB_EINVAL,
+               "spconv_tc_forward_planes: unsupported shape (c_red=%d n_out=%d taps=%d)", c_red, n_out, taps);
+  return launch_forward(nullptr, in_planes, num_in, c_red, packed, bias, nbr, num_out, taps, n_out, 2, relu, out_feats, stream_);
+}
+
+extern "C" int efgb_split_bf16(const float* in, int64_t rows, int channels, void* planes, efgb_stream_t stream_) {
+  cudaStream_t stream = as_stream(stream_);
+  EFGB_REQUIRE(rows >= 0 && channels >= 8 && channels % 8 == 0, EFGB_EINVAL, "split_bf16: channels must be a multiple of 8");
+  if (rows == 0) return EFGB_OK;
+  EFGB_REQUIRE(in && planes && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(planes) & 15) == 0,
+               EFGB_EINVAL, "split_bf16: null or misaligned pointer");
+  const int64_t units = rows * (channels / 8);
+  tc::split_bf16_kernel<<<grid_for(units, 256), 256, 0, stream>>>(in, rows, channels, reinterpret_cast<uint8_t*>(planes));
+  EFGB_LAUNCH_OK("split_bf16_kernel");
   return EFGB_OK;
 }
 
@@ -1183,18 +1492,10 @@ extern "C" int efgb_spconv_tc_wgrad(const float* in_feats, int64_t num_in, int c
   if (gx > p.num_items) gx = p.num_items;
   const dim3 grid(gx, n_slabs);
   if (split) {
-    static bool configured = false;
-    if (!configured) {
-      EFGB_CUDA_OK(cudaFuncSetAttribute(tc::spconv_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      configured = true;
-    }
+    EFGB_CUDA_OK(tc::ensure_max_smem(tc::spconv_wgrad_tc_kernel<true>, 3));
     tc::spconv_wgrad_tc_kernel<true><<<grid, tc::kThreads, smem, stream>>>(p, stages);
   } else {
-    static bool configured = false;
-    if (!configured) {
-      EFGB_CUDA_OK(cudaFuncSetAttribute(tc::spconv_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      configured = true;
-    }
+    EFGB_CUDA_OK(tc::ensure_max_smem(tc::spconv_wgrad_tc_kernel<false>, 4));
     tc::spconv_wgrad_tc_kernel<false><<<grid, tc::kThreads, smem, stream>>>(p, stages);
   }
   EFGB_LAUNCH_OK("spconv_wgrad_tc_kernel");

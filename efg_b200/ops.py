@@ -270,19 +270,39 @@ def spconv_forward(feats, w_kio, bias, nbr):
     return out
 
 
-# "fp32x3": tensor cores with the 3xTF32 split (fp32-faithful, default); "tf32": single-pass TF32;
+# "bf16x3" (default): three-product bf16 split for forward / dgrad (error ~2.5e-5, twice the MMA rate and half the operand
+# bytes of 3xTF32; wgrad stays on 3xTF32); "fp32x3": 3xTF32 split (error ~2^-21); "tf32": single-pass TF32;
 # "simt": exact fp32 FFMA kernel everywhere.
-CONV_PRECISION = "fp32x3"
+CONV_PRECISION = "bf16x3"
+_SPLIT_MODE = {"fp32x3": 1, "tf32": 0, "bf16x3": 2}
 
 
 def spconv_tc_supported(c_red, n_out, taps):
+    if CONV_PRECISION == "bf16x3" and c_red % 8 != 0:
+        return False
     return CONV_PRECISION != "simt" and c_red >= 16 and bool(_lib.lib().efgb_spconv_tc_supported(c_red, n_out, taps))
 
 
-def spconv_tc(feats, w_param, bias, nbr, mode, relu=False):
+def split_bf16(feats):
+    """fp32 [M, C] -> operand planes [M, 2, C] bf16 (hi, lo) for the pre-split tensor-core path; returned as an
+    opaque float32 tensor of the same shape as `feats` (same bytes per row)."""
+    _check(feats, "features", torch.float32)
+    planes = torch.empty_like(feats)
+    t0 = PROFILER.begin() if PROFILER is not None else None
+    _lib.check(_lib.lib().efgb_split_bf16(_p(feats), feats.shape[0], feats.shape[1], _p(planes), _stream()), "split_bf16")
+    if t0 is not None:
+        PROFILER.end("split_bf16", t0, 8 * feats.numel())
+    return planes
+
+
+# Pre-split planes pay off when a row is gathered many times (taps > 1); USE_PLANES=False keeps the in-producer split.
+USE_PLANES = True
+
+
+def spconv_tc(feats, w_param, bias, nbr, mode, relu=False, planes=None):
     """Tensor-core gather-GEMM.  w_param [c_out, taps, c_in] (reference layout), mode 0 fwd / 1 dgrad /
     2 dgrad-submanifold; feats [Mi, c_red]; returns [nbr.shape[0], N].  Fused epilogue: relu=True applies
-    max(x, 0) after the bias."""
+    max(x, 0) after the bias.  `planes`: the input already split by split_bf16 (bf16x3 only)."""
     _check(feats, "features", torch.float32)
     _check(w_param, "weight", torch.float32)
     c_out, taps, c_in = w_param.shape
@@ -295,27 +315,65 @@ def spconv_tc(feats, w_param, bias, nbr, mode, relu=False):
     if feats.shape[1] != c_red or (nbr is not None and nbr.shape[1] != taps):
         raise RuntimeError("spconv_tc: shape mismatch feats %r weight %r mode %d" %
                            (tuple(feats.shape), tuple(w_param.shape), mode))
-    split = 1 if CONV_PRECISION == "fp32x3" else 0
+    split = _SPLIT_MODE[CONV_PRECISION]
     L = _lib.lib()
     dev = feats.device
-    packed = torch.empty(L.efgb_spconv_tc_packed_bytes(taps, c_red, n_out, split) // 4, dtype=torch.float32, device=dev)
+    packed = packed_weights(w_param, mode, split)
     m_out = nbr.shape[0] if nbr is not None else feats.shape[0]
     out = torch.empty((m_out, n_out), dtype=torch.float32, device=dev)
-    t0 = PROFILER.begin() if PROFILER is not None else None
-    _lib.check(L.efgb_spconv_tc_pack(_p(w_param), c_out, taps, c_in, mode, split, _p(packed), _stream()), "spconv_tc_pack")
-    if t0 is not None:
-        PROFILER.end("spconv_pack_weights", t0, 4 * (w_param.numel() + packed.numel()))
-        t0 = PROFILER.begin()
     if bias is not None:
         _check(bias, "bias", torch.float32)
-    rc = L.efgb_spconv_tc_forward_ex(_p(feats), feats.shape[0], c_red, _p(packed), _p(bias), _p(nbr), m_out, taps, n_out,
-                                     split, 1 if relu else 0, _p(out), _stream())
+    use_planes = (split == 2 and nbr is not None and taps > 1 and USE_PLANES and feats.shape[0] > 0 and
+                  bool(L.efgb_spconv_tc_planes_supported(c_red, n_out, taps)))
+    if use_planes and planes is None:
+        planes = split_bf16(feats)
+    t0 = PROFILER.begin() if PROFILER is not None else None
+    if use_planes:
+        rc = L.efgb_spconv_tc_forward_planes(_p(planes), feats.shape[0], c_red, _p(packed), _p(bias), _p(nbr), m_out, taps,
+                                             n_out, 1 if relu else 0, _p(out), _stream())
+    else:
+        rc = L.efgb_spconv_tc_forward_ex(_p(feats), feats.shape[0], c_red, _p(packed), _p(bias), _p(nbr), m_out, taps,
+                                         n_out, split, 1 if relu else 0, _p(out), _stream())
     _lib.check(rc, "spconv_tc_forward")
     if t0 is not None:
         nbytes = 4 * (feats.shape[0] * c_red + m_out * n_out + taps * c_red * n_out + (taps * m_out if nbr is not None else 0))
         fam = ("spconv_tc_c%d" % max(c_red, n_out)) if nbr is not None else "dense_tc_gemm"
         PROFILER.end(fam, t0, nbytes, 2 * m_out * taps * c_red * n_out)
     return out
+
+
+# Packed weight images, cached per (parameter storage, version, mode, split): a parameter changes once per optimizer
+# step, so forward and dgrad of a layer and every micro-batch in between reuse the image (round 1 repacked on every
+# call: 82 pack launches per step).  Tensor._version increments on every in-place update (optimizer.step, load_state_dict).
+_PACK_CACHE = {}
+_PACK_CACHE_MAX = 512
+
+
+def packed_weights(w_param, mode, split):
+    c_out, taps, c_in = w_param.shape
+    n_out, c_red = (c_out, c_in) if mode == 0 else (c_in, c_out)
+    base = w_param._base if w_param._base is not None else w_param   # views of a Parameter share its version counter
+    key = (w_param.data_ptr(), tuple(w_param.shape), mode, split, w_param.device.index)
+    ver = base._version
+    hit = _PACK_CACHE.get(key)
+    if hit is not None and hit[0] == ver and hit[2]() is base:   # same tensor object, not updated in place since
+        return hit[1]
+    L = _lib.lib()
+    packed = torch.empty(L.efgb_spconv_tc_packed_bytes(taps, c_red, n_out, split) // 4, dtype=torch.float32, device=w_param.device)
+    t0 = PROFILER.begin() if PROFILER is not None else None
+    _lib.check(L.efgb_spconv_tc_pack(_p(w_param), c_out, taps, c_in, mode, split, _p(packed), _stream()), "spconv_tc_pack")
+    if t0 is not None:
+        PROFILER.end("spconv_pack_weights", t0, 4 * (w_param.numel() + packed.numel()))
+    if len(_PACK_CACHE) >= _PACK_CACHE_MAX:
+        _PACK_CACHE.clear()
+    _PACK_CACHE[key] = (ver, packed, weakref.ref(base))
+    return packed
+
+
+def clear_pack_cache():
+    """Drop every cached weight image (needed only after writing a weight through `.data`, which bypasses the
+    version counter the cache is keyed on)."""
+    _PACK_CACHE.clear()
 
 
 def spconv_tc_wgrad_supported(c_in, c_out, taps):
@@ -331,7 +389,7 @@ def spconv_tc_wgrad(feats, grad_out, nbr, taps, c_in, c_out):
     m_out = nbr.shape[0] if nbr is not None else grad_out.shape[0]
     dw = torch.empty((c_out, taps, c_in), dtype=torch.float32, device=feats.device)
     L = _lib.lib()
-    split = 1 if CONV_PRECISION == "fp32x3" else 0
+    split = 0 if CONV_PRECISION == "tf32" else 1  # bf16x3 keeps the weight gradients on 3xTF32
     t0 = PROFILER.begin() if PROFILER is not None else None
     rc = L.efgb_spconv_tc_wgrad(_p(feats), feats.shape[0], c_in, _p(grad_out), _p(nbr), m_out, taps, c_out, split,
                                 _p(dw), _stream())

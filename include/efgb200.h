@@ -150,15 +150,17 @@ int efgb_spconv_forward(const float* in_feats, int64_t num_in, int c_in,
                         float* out_feats, efgb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
- * Tensor-core path of the same gather-GEMM (tcgen05.mma kind::tf32, accumulators in TMEM, weights
- * streamed by the TMA engine).  Weights are given in the reference parameter layout
+ * Tensor-core path of the same gather-GEMM (tcgen05.mma kind::tf32 / kind::f16, accumulators in TMEM, weights
+ * streamed with cp.async.bulk — the bulk-copy engine without a tensor map).  Weights are given in the reference parameter layout
  * [c_out, taps, c_in] (spconv 2.x, taps = kd*kh*kw flattened) and packed once per call into the
  * shared-memory image the tensor core reads:
  *   mode 0 forward            N = c_out, reduction channels c_red = c_in
  *   mode 1 dgrad (regular)    N = c_in,  c_red = c_out   (use with nbr_t)
  *   mode 2 dgrad (submanifold, tap order mirrored; use with the forward nbr)
- * split != 0 selects 3xTF32 (fp32-faithful, error ~2^-21); split == 0 single-pass TF32.
- * Supported when c_red % 4 == 0, 16 <= N <= 256, N % 16 == 0, taps <= 32.
+ * split: 0 single-pass TF32; 1 3xTF32 (fp32-faithful, error ~2^-21); 2 bf16x3 (three bf16 products on kind::f16,
+ * error ~2.5e-5, needs c_red % 8 == 0) — the packed image differs per split.
+ * Supported when c_red % 4 == 0, N % 16 == 0, 16 <= N <= 256 or N a multiple of 256 up to 4096 (256-column slabs
+ * over grid.y), taps <= 32.
  * ------------------------------------------------------------------------------------------ */
 int efgb_spconv_tc_supported(int c_red, int n_out, int taps);
 size_t efgb_spconv_tc_packed_bytes(int taps, int c_red, int n_out, int split);
@@ -175,10 +177,24 @@ int efgb_spconv_tc_forward_ex(const float* in_feats, int64_t num_in, int c_red, 
                               const float* bias, const int32_t* nbr, int64_t num_out, int taps, int n_out,
                               int split, int relu, float* out_feats, efgb_stream_t stream);
 
+/* Pre-split operand planes (bf16x3): a gathered input row is read by ~14 output rows of a 3x3x3 convolution, so the
+ * fp32 -> bf16 hi / lo split is done ONCE per feature matrix instead of once per gather.
+ *   efgb_split_bf16: in [rows, channels] f32 -> planes [rows][hi channels x bf16 | lo channels x bf16]
+ *                    (same bytes per row as fp32; channels % 8 == 0)
+ *   efgb_spconv_tc_forward_planes: the bf16x3 gather-GEMM over such planes (weights packed with split = 2); the A
+ *                    producers are cp.async copies with zero fill for missing neighbours.  Needs a rulebook
+ *                    (sparse convolutions; dense GEMMs read every row once and keep the fp32 entry point).
+ * Replaces the same spconv call sites as efgb_spconv_tc_forward (sparse_net.py:85-95,125-147). */
+int efgb_split_bf16(const float* in, int64_t rows, int channels, void* planes, efgb_stream_t stream);
+int efgb_spconv_tc_planes_supported(int c_red, int n_out, int taps);
+int efgb_spconv_tc_forward_planes(const void* in_planes, int64_t num_in, int c_red, const float* packed,
+                                  const float* bias /* nullable */, const int32_t* nbr, int64_t num_out, int taps,
+                                  int n_out, int relu, float* out_feats, efgb_stream_t stream);
+
 /* Tensor-core wgrad: dw_param[co, tap, ci] = sum_o in[nbr[o,tap], ci] * grad_out[o, co], written in the
  * reference parameter layout [c_out, taps, c_in] (zero-filled by the callee, accumulated with
  * red.global.add).  Supported when c_in divides 128 or is a multiple of 128 (>= 16) and c_out % 16 == 0,
- * c_out <= 256. */
+ * c_out <= 256 or a multiple of 256 up to 4096 (256-column slabs). */
 int efgb_spconv_tc_wgrad_supported(int c_in, int c_out, int taps);
 int efgb_spconv_tc_wgrad(const float* in_feats, int64_t num_in, int c_in, const float* grad_out,
                          const int32_t* nbr, int64_t num_out, int taps, int c_out, int split,

@@ -182,11 +182,13 @@ def test_box3d_attention_merged_projection_matches_torch_chain(with_rotation):
             # d(bilinear sample)/d(location) is piecewise constant per BEV cell: a sampling location that lands within
             # 1 ulp of a cell border may floor() to the other cell in one of the two implementations, which changes
             # that query's gradient by O(1).  Allow a vanishing fraction of such rows, require the rest to agree.
-            bad_rows = (diff.amax(-1) > 2e-4 * scale).float().mean().item()
-            assert bad_rows < 2e-3, (n, bad_rows)
+            bad_rows = (diff.amax(-1) > 1e-3 * scale).float().mean().item()
+            assert bad_rows < 5e-3, (n, bad_rows)
         elif n in ("dW_box", "db_box"):
             # ... and those few rows enter the box-projection gradients, which sum over all rows
             rel = (diff.norm() / a.norm().clamp_min(1e-12)).item()
             assert rel < 5e-3, (n, rel)
         else:
-            assert diff.max().item() < 2e-4 * scale, (n, diff.max().item(), scale)
+            # the merged projection runs on the tensor cores in the default bf16x3 mode (error ~2.5e-5 relative per GEMM);
+            # the bar is north_star's 1e-3
+            assert diff.max().item() < 1e-3 * scale, (n, diff.max().item(), scale)
