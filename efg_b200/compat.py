@@ -35,6 +35,10 @@ def _ensure_package(name):
 
 
 def install(force=False):
+    """Register the aliases.  A REAL `efg` package on sys.path (the reference checkout) is never shadowed: it is
+    imported and only the pieces it lacks are attached to it — `efg._C` (the reference builds it as a CUDAExtension,
+    setup.py:63-71; here the C-ABI library stands in) and `efg.modeling.operators` (imported by
+    VD/modules/box_attention.py:7 but absent from the tree).  Without a real `efg`, a namespace stub carries the aliases."""
     from . import _C, operators, spconv
     from .spconv import pytorch as spconv_pytorch
 
@@ -43,7 +47,25 @@ def install(force=False):
         sys.modules["spconv"] = spconv
         sys.modules["spconv.pytorch"] = spconv_pytorch
         installed += ["spconv", "spconv.pytorch"]
-    if force or _missing("efg"):
+    real_efg = None
+    if not force and not _missing("efg") and "efg" not in sys.modules:
+        real_efg = importlib.import_module("efg")
+    elif "efg" in sys.modules and getattr(sys.modules["efg"], "__file__", None):
+        real_efg = sys.modules["efg"]
+    if real_efg is not None:
+        if _missing("efg._C"):
+            sys.modules["efg._C"] = _C
+            real_efg._C = _C
+            installed.append("efg._C")
+        try:
+            modeling = importlib.import_module("efg.modeling")
+        except ImportError:
+            modeling = _ensure_package("efg.modeling")
+        if _missing("efg.modeling.operators"):
+            sys.modules["efg.modeling.operators"] = operators
+            modeling.operators = operators
+            installed.append("efg.modeling.operators")
+    else:
         efg = _ensure_package("efg")
         _ensure_package("efg.modeling")
         for alias, target in (("efg._C", _C), ("efg.operators", operators), ("efg.modeling.operators", operators)):

@@ -179,7 +179,9 @@ class ConQueR(VoxelDETR):
             suffix = "_dn" if li == len(layers) - 1 else "_dn_{}".format(li)
             for loss in head.losses.losses:
                 for k, v in head.losses.det3d_losses[loss](lo, targets, match, num_boxes * groups).items():
-                    out[k + suffix] = v * weights.get(k, 1.0)
+                    # the reference's weight_dict holds the base, `_enc` and `_{i}` keys only (CQ/heads.py), so every
+                    # denoising loss keeps weight 1 (pinned by tests/golden/model_conquer.pt)
+                    out[k + suffix] = v * weights.get(k + suffix, 1.0)
         return out
 
     def contrastive_losses(self, cls_out, box_out, final_match, targets, dn_meta):

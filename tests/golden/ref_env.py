@@ -40,6 +40,17 @@ STUBBABLE = {"portalocker", "pycocotools", "termcolor", "pyquaternion", "nuscene
              "fvcore", "iopath", "timm", "numba_stub_never"}
 
 
+# stubbed even though a module of that name is installed (the image's cv2 raises on import: cv2.dnn.DictValue)
+FORCE_STUB = {"cv2"}
+
+
+class _ForceStubFinder(importlib.abc.MetaPathFinder):
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname.split(".")[0] in FORCE_STUB:
+            return importlib.machinery.ModuleSpec(fullname, _StubFinder(), is_package=True)
+        return None
+
+
 def available():
     return os.path.isdir(os.path.join(REF, "efg"))
 
@@ -156,6 +167,8 @@ def install(spconv_module=None, c_module=None, box_attn_function=None):
         del sys.modules[name]
     sys.path.insert(0, REF)
     sys.meta_path.append(_installed["finder"])
+    _installed["force"] = _ForceStubFinder()
+    sys.meta_path.insert(0, _installed["force"])
     import collections
     import collections.abc
     for name in ("Mapping", "MutableMapping", "Sequence", "Iterable", "Callable"):  # removed from `collections` in py3.10
@@ -189,17 +202,34 @@ def install(spconv_module=None, c_module=None, box_attn_function=None):
     import efg.modeling as efg_modeling  # namespace package inside the reference
 
     efg_modeling.operators = ops_alias
+    # CP/voxelnet.py:9 imports `efg.data.augmentations3d._dict_select`, a module the reference tree no longer has;
+    # the function lives in efg/data/utils/misc.py:1-9 (SURVEY.md §8b import closure)
+    import efg.data.utils.misc as _misc
+
+    aug3d = types.ModuleType("efg.data.augmentations3d")
+    aug3d._dict_select = _misc._dict_select
+    sys.modules["efg.data.augmentations3d"] = aug3d
 
 
 def uninstall():
     if not _installed:
         return
     sys.meta_path.remove(_installed["finder"])
+    sys.meta_path.remove(_installed["force"])
     sys.path[:] = _installed["path"]
+    # drop what install() put in place (the reference's efg package, the aliases and the stubs); real third-party
+    # modules imported meanwhile (cv2, numba, ...) stay loaded: C extensions do not survive a second import
     for name in list(sys.modules):
-        if name not in _installed["modules"]:
+        top = name.split(".")[0]
+        if name in _installed["modules"]:
+            continue
+        mod = sys.modules[name]
+        if top in ("efg", "spconv") or isinstance(mod, _StubModule) or top in STUBBABLE or \
+                (top == "omegaconf" and not hasattr(mod, "__file__")) or name == "torch._six":
             del sys.modules[name]
-    sys.modules.update(_installed["modules"])
+    for name, mod in _installed["modules"].items():
+        if name.split(".")[0] in ("efg", "spconv"):
+            sys.modules[name] = mod
     _installed.clear()
 
 
@@ -218,6 +248,30 @@ def reference_box_attn_function():
             return mod.ms_deform_attn_core_pytorch(value, spatial_shapes, sampling_locations, attn)
 
     return BoxAttnFunction
+
+
+@contextlib.contextmanager
+def cuda_calls_stay_on_cpu():
+    """The ConQueR playground hard-codes `.cuda()` / `.to("cuda")` on freshly created tensors (CQ/cdn.py:20-94,
+    CQ/losses.py:161-167).  To run those unmodified files on the CPU of this container the two calls become no-ops
+    for the duration of the block (an environment shim, like the missing third-party modules above)."""
+    import torch
+
+    orig_cuda, orig_to = torch.Tensor.cuda, torch.Tensor.to
+
+    def to(self, *a, **k):
+        a = tuple(x for x in a if not (isinstance(x, str) and x.startswith("cuda")) and
+                  not (isinstance(x, torch.device) and x.type == "cuda"))
+        if isinstance(k.get("device"), (str, torch.device)) and str(k["device"]).startswith("cuda"):
+            k = {kk: v for kk, v in k.items() if kk != "device"}
+        return orig_to(self, *a, **k) if (a or k) else self
+
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.Tensor.to = to
+    try:
+        yield
+    finally:
+        torch.Tensor.cuda, torch.Tensor.to = orig_cuda, orig_to
 
 
 @contextlib.contextmanager

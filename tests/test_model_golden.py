@@ -1,0 +1,281 @@
+"""Model-level parity against goldens produced by the REFERENCE's own model code.
+
+tests/golden/model_{voxel_detr,conquer,centerpoint}.pt were written by tests/golden/make_golden_model.py, which runs the
+unmodified playground files (net.build_model -> VoxelDETR / ConQueR VoxelDETR / VoxelNet: transformer, heads, losses,
+matcher, box coder, position encoding, box attention module, CDN, contrastive loss, centre head, CenterNet loss, label
+assignment) and efg/modeling/backbones/{sparse_net,fpn,configurable_rpn}.py on seeded scenes with weights that are a
+function of the parameter names.  Here the efg_b200 classes must
+
+  * expose exactly the reference's state_dict keys and shapes (so reference checkpoints load 1:1),
+  * reproduce the training losses (CPU oracle backend: <= 2e-5 relative; CUDA kernels: <= 1e-3, north_star's bar),
+  * reproduce the gradients of parameters from every part of the graph,
+  * reproduce the eval-mode detections.
+
+A wrong loss weight, focal alpha, matcher cost term, box-coder normalisation, sine-embedding order, CDN group layout or
+gaussian radius fails these tests.  When /root/reference is present the same comparison also runs live
+(test_live_reference_*), so the goldens cannot go stale silently.
+"""
+import copy
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import model_cases as mc  # noqa: E402
+import ref_env  # noqa: E402
+
+KINDS = ["voxel_detr", "conquer", "centerpoint"]
+
+
+def load_golden(kind):
+    return torch.load(os.path.join(HERE, "golden", "model_%s.pt" % kind), weights_only=False)
+
+
+def build_port(kind, device="cpu", backend=None):
+    cfg = mc.make_config(kind, device)
+    if kind == "voxel_detr":
+        from efg_b200.detectors.voxel_detr import VoxelDETR as cls
+    elif kind == "conquer":
+        from efg_b200.detectors.conquer import ConQueR as cls
+    else:
+        from efg_b200.detectors.centerpoint import VoxelNet as cls
+    torch.manual_seed(0)
+    model = cls(cfg, backend=backend) if backend is not None else cls(cfg)
+    return cfg, model
+
+
+def cdn_noise_from_draws(d, label_noise_ratio):
+    """The reference draws `new_label` only for the chosen rows (CQ/cdn.py:40-42); the port takes one value per row."""
+    chosen = d["p_label"] < label_noise_ratio * 0.5
+    new_label = torch.zeros(d["p_label"].shape[0], dtype=torch.int64)
+    new_label[chosen] = d["new_label_chosen"].to(torch.int64)
+    return {"p_label": d["p_label"], "new_label": new_label, "rand_sign": d["rand_sign"] * 2.0 - 1.0,
+            "rand_part": d["rand_part"]}
+
+
+def run_port_train(kind, g, device="cpu", backend=None):
+    cfg, model = build_port(kind, device, backend)
+    model.load_state_dict(mc.fill_state_dict(model.state_dict()))
+    model.train()
+    if kind == "conquer":
+        model.cdn_noise = cdn_noise_from_draws(g["cdn_draws"], cfg.model.dn.dn_label_noise_ratio)
+    losses = model(mc.make_batch(g["scenes"], cfg.dataset))
+    total = sum(v for k, v in losses.items() if "loss" in k and v.requires_grad)
+    total.backward()
+    grads = {n: p.grad.detach().cpu() for n, p in model.named_parameters() if p.grad is not None}
+    return cfg, model, {k: float(v.detach()) for k, v in losses.items()}, grads
+
+
+def check_losses(got, exp, rel):
+    assert set(got) == set(exp), (sorted(set(got) ^ set(exp)))
+    for k, v in exp.items():
+        assert abs(got[k] - v) <= rel * max(1.0, abs(v)), (k, got[k], v)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_state_dict_keys_match_reference(kind):
+    g = load_golden(kind)
+    _, model = build_port(kind, backend=_cpu_backend())
+    mine = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert mine == g["state_dict_shapes"], sorted(set(mine.items()) ^ set(g["state_dict_shapes"].items()))[:10]
+
+
+def _cpu_backend():
+    from oracle.backend_cpu import cpu_backend
+
+    return cpu_backend()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_train_losses_and_grads_match_reference_golden_cpu(kind):
+    g = load_golden(kind)
+    _, model, losses, grads = run_port_train(kind, g, backend=_cpu_backend())
+    check_losses(losses, g["losses"], 2e-5)
+    # parameters without a gradient: the reference leaves more of them untouched only where this repo prunes
+    # FPN levels nobody reads (checked equal in test_model_cpu.py); every parameter the reference trains gets a gradient here
+    for name in g["grad_norms"]:
+        if name not in grads:
+            assert g["grad_norms"][name] == 0.0 or "fpn" in name or "lateral" in name or "top_block" in name, name
+    for name, ref_grad in g["grads"].items():
+        scale = max(ref_grad.abs().max().item(), 1e-6)
+        err = (grads[name] - ref_grad).abs().max().item()
+        assert err <= 2e-3 * scale, (name, err, scale)
+    for name, n in g["grad_norms"].items():
+        if name in grads and n > 1e-6:
+            assert abs(grads[name].norm().item() - n) <= 5e-3 * n, (name, grads[name].norm().item(), n)
+
+
+@pytest.mark.parametrize("kind", ["voxel_detr", "conquer"])
+def test_eval_detections_match_reference_golden_cpu(kind):
+    g = load_golden(kind)
+    cfg, model = build_port(kind, backend=_cpu_backend())
+    model.load_state_dict(mc.fill_state_dict(model.state_dict()))
+    model.eval()
+    with torch.no_grad():
+        res = model(mc.make_batch(g["scenes"][:1], cfg.dataset))
+    _compare_detections(res, g["eval"], 1e-5)
+
+
+def _compare_detections(res, exp, tol):
+    assert len(res) == len(exp)
+    for r, e in zip(res, exp):
+        assert r["scores"].shape == e["scores"].shape, (r["scores"].shape, e["scores"].shape)
+        # topk(sorted=False) leaves the order unspecified (VD/voxel_detr.py:183): compare as sets, by descending score
+        oi, oe = torch.argsort(r["scores"].cpu(), descending=True, stable=True), torch.argsort(e["scores"], descending=True, stable=True)
+        assert torch.allclose(r["scores"].cpu()[oi], e["scores"][oe], atol=tol)
+        # ties / near-ties may permute: labels and boxes are compared where the score gap to the neighbours is clear
+        s = e["scores"][oe]
+        gap = torch.ones_like(s, dtype=torch.bool)
+        gap[1:] &= (s[:-1] - s[1:]) > 10 * tol
+        gap[:-1] &= (s[:-1] - s[1:]) > 10 * tol
+        assert gap.float().mean() > 0.5
+        assert torch.equal(r["labels"].cpu()[oi][gap], e["labels"][oe][gap])
+        assert torch.allclose(r["boxes3d"].cpu()[oi][gap], e["boxes3d"][oe][gap], atol=max(tol * 100, 1e-4))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# live: the reference's own files, imported from /root/reference (skipped on the GPU box)
+# ---------------------------------------------------------------------------------------------------------------
+needs_reference = pytest.mark.skipif(not ref_env.available(), reason="/root/reference is not present")
+
+
+@needs_reference
+def test_live_reference_voxel_detr_equals_port_and_golden():
+    """Unmodified VD/net.py:build_model over the spconv / BoxAttnFunction shims, same weights, same scenes:
+    losses equal the port's to 2e-5 and equal the committed golden (so the golden is what the reference computes today)."""
+    from oracle import spconv_cpu
+
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_golden_model as mg
+
+    g = load_golden("voxel_detr")
+    fresh = mg.run_reference("voxel_detr")
+    check_losses(fresh["losses"], g["losses"], 1e-6)
+    assert fresh["state_dict_shapes"] == g["state_dict_shapes"]
+    _, _, losses, _ = run_port_train("voxel_detr", g, backend=_cpu_backend())
+    check_losses(losses, fresh["losses"], 2e-5)
+    assert spconv_cpu is not None
+
+
+def _voxel_inputs(scenes, dataset_cfg, nfeat):
+    """(mean voxel features [M, nfeat], coords [M, 4] (b, z, y, x), batch, grid (x, y, z))."""
+    from oracle import voxelize as ov
+
+    feats, coords = [], []
+    for b, (pts, _) in enumerate(scenes):
+        v, c, n = ov.hard_voxelize(pts, dataset_cfg["voxel_size"], dataset_cfg["pc_range"], 5, 20000)
+        feats.append(ov.mean_vfe(v, n)[:, :nfeat])
+        coords.append(np.concatenate([np.full((c.shape[0], 1), b, np.int32), c], 1))
+    grid = ov.grid_size(dataset_cfg["voxel_size"], dataset_cfg["pc_range"]).astype(np.int64)
+    return torch.from_numpy(np.concatenate(feats)), torch.from_numpy(np.concatenate(coords)), len(scenes), grid
+
+
+@needs_reference
+@pytest.mark.parametrize("which", ["SpMiddleResNetFHD", "SparseResNet"])
+def test_live_reference_sparse_backbones_run_over_the_spconv_surface(which):
+    """The reference's efg/modeling/backbones/sparse_net.py (SpMiddleResNetFHD :472-545, SparseResNet :239-309 via
+    build_sparse_resnet_backbone :318-397) imports and runs UNMODIFIED over a module exposing the `spconv.pytorch`
+    surface this repo implements (on the CPU: its oracle twin, same class names / arguments / weight layout), and
+    efg_b200/modeling/sparse_backbone.py produces the same BEV maps from the same state_dict."""
+    from oracle import spconv_cpu
+    from oracle.backend_cpu import cpu_backend
+    from efg_b200.modeling import sparse_backbone as port
+
+    kind = "centerpoint" if which == "SpMiddleResNetFHD" else "voxel_detr"
+    cfg = mc.make_config(kind)
+    feats, coords, batch, grid = _voxel_inputs(mc.make_scenes(kind), cfg.dataset, 5)
+    with ref_env.playground(ref_env.CP_DIR, spconv_module=spconv_cpu):
+        from efg.modeling.backbones import sparse_net as ref_sn
+
+        torch.manual_seed(0)
+        if which == "SpMiddleResNetFHD":
+            ref_mod = ref_sn.SpMiddleResNetFHD(num_input_features=5, norm="BN1d")
+            mine = port.SpMiddleResNetFHD(num_input_features=5, norm="BN1d", backend=cpu_backend())
+        else:
+            rcfg = ref_env.to_cfg(copy.deepcopy(dict(cfg.model.sparse_resnets)))
+            ref_mod = ref_sn.build_sparse_resnet_backbone(rcfg, 5)
+            mine = port.build_sparse_resnet_backbone(cfg.model.sparse_resnets, 5, backend=cpu_backend())
+        sd = mc.fill_state_dict(ref_mod.state_dict())
+        ref_mod.load_state_dict(sd)
+        ref_mod.train()
+        ref_out = ref_mod(feats, coords, batch, grid)
+    assert {k: tuple(v.shape) for k, v in mine.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+    mine.load_state_dict(sd)
+    mine.train()
+    out = mine(feats, coords, batch, grid)
+    if isinstance(ref_out, dict):
+        assert set(out) >= {k for k in ref_out}, (sorted(out), sorted(ref_out))
+        pairs = [(out[k], ref_out[k]) for k in ref_out]
+    else:
+        ref_list = ref_out if isinstance(ref_out, (list, tuple)) else [ref_out]
+        out_list = out if isinstance(out, (list, tuple)) else [out]
+        pairs = [(a, b) for a, b in zip(out_list, ref_list) if torch.is_tensor(b)]
+        assert pairs
+    for a, b in pairs:
+        assert a.shape == b.shape
+        assert (a - b).abs().max().item() <= 1e-5 * max(1.0, b.abs().max().item())
+
+
+@needs_reference
+@pytest.mark.parametrize("kind", KINDS)
+def test_live_reference_playground_builds_over_the_product_surface(kind):
+    """`from net import build_model` of the unmodified playground directory resolves `spconv.pytorch`, `efg._C` and
+    `efg.modeling.operators.BoxAttnFunction` to THIS repo's product modules (efg_b200.spconv / _C / operators — the CUDA
+    path, no oracle) and constructs the reference model: every constructor call the reference makes on the spconv
+    surface (argument names, int / list / tuple kernel sizes, strides, paddings, indice_key, bias) is accepted and the
+    parameter layout is the reference's.  (Executing it needs a GPU; this container has none and the GPU box has no
+    /root/reference — the executed comparison is the golden test above.)"""
+    import efg_b200._C as product_c
+    import efg_b200.spconv as product_spconv
+    from efg_b200.operators import BoxAttnFunction
+
+    g = load_golden(kind)
+    cfg = mc.make_config(kind)
+    exp_dir = {"voxel_detr": ref_env.VD_DIR, "conquer": ref_env.CQ_DIR, "centerpoint": ref_env.CP_DIR}[kind]
+    with ref_env.playground(exp_dir, spconv_module=product_spconv, c_module=product_c, box_attn_function=BoxAttnFunction):
+        from net import build_model
+        import efg
+
+        assert os.path.realpath(efg.__file__).startswith(ref_env.REF)   # the real package, not a stub
+        model = build_model(None, ref_env.to_cfg(copy.deepcopy(dict(cfg))))
+        shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+        convs = [m for m in model.modules() if isinstance(m, (product_spconv.SubMConv3d, product_spconv.SparseConv3d))]
+    assert shapes == g["state_dict_shapes"]
+    assert len(convs) >= 20
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU: the CUDA kernels behind the same classes against the same reference goldens
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", KINDS)
+def test_train_losses_match_reference_golden_gpu(kind):
+    """Whole model on the CUDA path (voxelizer, rulebooks, tcgen05 sparse conv in the default bf16x3 mode, box attention,
+    device Hungarian, fused layers) vs the REFERENCE's losses: within north_star's 1e-3."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = load_golden(kind)
+    _, _, losses, grads = run_port_train(kind, g, device="cuda")
+    check_losses(losses, g["losses"], 1e-3)
+    for name, ref_grad in g["grads"].items():
+        scale = max(ref_grad.abs().max().item(), 1e-6)
+        # whole-model gradients at random initialisation amplify rounding (DESIGN.md §5 note 2): 5 % of the largest entry
+        assert (grads[name] - ref_grad).abs().max().item() <= 5e-2 * scale, name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["voxel_detr", "conquer"])
+def test_eval_detections_match_reference_golden_gpu(kind):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = load_golden(kind)
+    cfg, model = build_port(kind, device="cuda")
+    model.load_state_dict(mc.fill_state_dict(model.state_dict()))
+    model.eval()
+    with torch.no_grad():
+        res = model(mc.make_batch(g["scenes"][:1], cfg.dataset))
+    _compare_detections(res, g["eval"], 1e-3)
