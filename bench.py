@@ -227,11 +227,12 @@ def run_efgb200(args):
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step(batch):
-        opt.zero_grad(set_to_none=True)
+        averager.zero_grad()          # one memset per gradient bucket; p.grad are views into the buckets
         losses = model([({"points": p}, {"annotations": a}) for p, a in batch])
         total = sum(v for k, v in losses.items() if k.startswith("loss"))
-        total.backward()
-        averager.average_gradients()
+        total.backward()              # bucket all-reduces are launched from inside backward (post-accumulate hooks)
+        averager.finish()
+        averager.hide_unused()        # parameters of pruned branches keep grad = None, as under DDP
         opt.step()
         return total
 

@@ -54,6 +54,8 @@ SIGNATURES = {
     "efgb_dense_to_sparse": (_int, [_vp, _vp, _i64, _int, _int, _host_i32x3, _vp, _vp]),
     "efgb_lsa_batched": (_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
                                 ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64), _int, _vp, _vp, _vp]),
+    "efgb_lsa_batched_status": (_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+                                       ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64), _int, _vp, _vp, _vp, _vp]),
     "efgb_add_layernorm_supported": (_int, [_int]),
     "efgb_add_layernorm_workspace_bytes": (_sz, [_i64, _int]),
     "efgb_add_layernorm_forward": (_int, [_vp, _vp, _vp, _vp, _i64, _int, ctypes.c_float, _vp, _vp, _vp, _vp, _vp]),

@@ -42,7 +42,8 @@ __device__ __forceinline__ bool lsa_better(double oval, int oit, bool oun, doubl
 }
 
 __global__ void __launch_bounds__(32)
-lsa_kernel(const LsaBatch batch, long long* __restrict__ out_rows, long long* __restrict__ out_cols, int cost_in_smem) {
+lsa_kernel(const LsaBatch batch, long long* __restrict__ out_rows, long long* __restrict__ out_cols, int cost_in_smem,
+           int* __restrict__ status) {
   const LsaProblem pr = batch.p[blockIdx.x];
   const int lane = threadIdx.x;
   const bool tr = pr.cols < pr.rows;
@@ -170,6 +171,23 @@ lsa_kernel(const LsaBatch batch, long long* __restrict__ out_rows, long long* __
     __syncwarp();
   }
 
+  // Infeasible problem (non-finite costs; scipy raises "matrix contains invalid numeric entries" / "cost matrix is
+  // infeasible"): flag it for the caller and complete the assignment with the free columns in ascending order, so
+  // that every pair written below is a valid index — a diverged step must surface as a clean exception on the host
+  // (ops.lsa_status), not as an out-of-bounds gather in the losses.
+  if (lane == 0) {
+    int next_free = 0, bad = 0;
+    for (int r = 0; r < nr; ++r) {
+      if (col4row[r] >= 0) continue;
+      bad = 1;
+      while (next_free < nc && row4col[next_free] >= 0) ++next_free;
+      col4row[r] = next_free;
+      row4col[next_free] = r;
+    }
+    if (bad && status) atomicOr(status, 1);
+  }
+  __syncwarp();
+
   // pairs sorted by the ORIGINAL row index, as scipy returns them
   long long* orow = out_rows + pr.out_off;
   long long* ocol = out_cols + pr.out_off;
@@ -200,18 +218,33 @@ static size_t lsa_smem_bytes(int rows, int cols, bool with_cost) {
 
 using namespace efgb;
 
+extern "C" int efgb_lsa_batched_status(const void* const* cost_ptrs_host, const int32_t* rows_host, const int32_t* cols_host,
+                                       const int32_t* ld_host, const int64_t* out_offsets_host, int count, int64_t* out_rows,
+                                       int64_t* out_cols, int32_t* status, efgb_stream_t stream_);
+
 extern "C" int efgb_lsa_batched(const void* const* cost_ptrs_host, const int32_t* rows_host, const int32_t* cols_host,
                                 const int32_t* ld_host, const int64_t* out_offsets_host, int count, int64_t* out_rows,
                                 int64_t* out_cols, efgb_stream_t stream_) {
+  return efgb_lsa_batched_status(cost_ptrs_host, rows_host, cols_host, ld_host, out_offsets_host, count, out_rows, out_cols,
+                                 nullptr, stream_);
+}
+
+extern "C" int efgb_lsa_batched_status(const void* const* cost_ptrs_host, const int32_t* rows_host, const int32_t* cols_host,
+                                       const int32_t* ld_host, const int64_t* out_offsets_host, int count, int64_t* out_rows,
+                                       int64_t* out_cols, int32_t* status, efgb_stream_t stream_) {
   cudaStream_t stream = as_stream(stream_);
   EFGB_REQUIRE(count >= 0, EFGB_EINVAL, "lsa_batched: negative count");
   if (count == 0) return EFGB_OK;
   EFGB_REQUIRE(cost_ptrs_host && rows_host && cols_host && ld_host && out_offsets_host && out_rows && out_cols, EFGB_EINVAL,
                "lsa_batched: null pointer");
-  static bool configured = false;
-  if (!configured) {
-    EFGB_CUDA_OK(cudaFuncSetAttribute(lsa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
+  {
+    static unsigned char configured[64] = {};   // per device: the attribute belongs to the device's context
+    int dev = 0;
+    EFGB_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+      EFGB_CUDA_OK(cudaFuncSetAttribute(lsa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      if (dev >= 0 && dev < 64) configured[dev] = 1;
+    }
   }
   for (int base = 0; base < count; base += kLsaMaxBatch) {
     const int n = count - base < kLsaMaxBatch ? count - base : kLsaMaxBatch;
@@ -235,7 +268,7 @@ extern "C" int efgb_lsa_batched(const void* const* cost_ptrs_host, const int32_t
     const size_t smem = in_smem ? smem_cost : smem_plain;
     EFGB_REQUIRE(smem <= 227 * 1024, EFGB_EINVAL, "lsa_batched: a problem is too large for one CTA (%zu bytes of state)", smem);
     lsa_kernel<<<n, 32, smem, stream>>>(batch, reinterpret_cast<long long*>(out_rows), reinterpret_cast<long long*>(out_cols),
-                                        in_smem ? 1 : 0);
+                                        in_smem ? 1 : 0, status);
     EFGB_LAUNCH_OK("lsa_kernel");
   }
   return EFGB_OK;

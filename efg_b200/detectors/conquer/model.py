@@ -27,8 +27,8 @@ class ConQueRTransformer(Transformer):
 
     @torch.no_grad()
     def _momentum_update_gt_decoder(self):
-        q = [p.data for p in self.decoder.parameters()]
-        k = [p.data for p in self.decoder_gt.parameters()]
+        q = [p.detach() for p in self.decoder.parameters()]
+        k = [p for p in self.decoder_gt.parameters()]   # in place on the parameters: bumps their version counters
         torch._foreach_mul_(k, self.m)
         torch._foreach_add_(k, q, alpha=1.0 - self.m)
 
@@ -92,6 +92,8 @@ class ConQueR(VoxelDETR):
 
     def forward(self, batched_inputs):
         targets = self.encode_targets(batched_inputs) if self.training else None
+        if targets is not None:
+            self.transformer.proposal_head.losses.request_normaliser(targets, self.device)
         features, pos = self.extract(batched_inputs)
         dn = self.config.model.dn
         if self.training and dn.enabled and dn.dn_number > 0:
@@ -121,7 +123,7 @@ class ConQueR(VoxelDETR):
         nq = self.num_queries
         prop, head = self.transformer.proposal_head, self.transformer.decoder.detection_head
         num_boxes = prop.losses.normaliser(targets, cls_out.device)
-        cached = getattr(self.transformer, "_enc_head_out", None)  # see VoxelDETR.losses
+        cached = getattr(self.transformer, "_enc_head_out", None) if self.reuse_proposal_head else None  # see VoxelDETR.losses
         enc_cls, enc_box = cached if cached is not None else prop(memory, anchors)
         self.transformer._enc_head_out = None
         bin_targets = TargetList(dict(t, labels=torch.zeros_like(t["labels"])) for t in targets)

@@ -66,17 +66,23 @@ def device_matches(mats, num_layers, offsets, device):
 
     rows, cols, sizes = ops.lsa_batched(mats)
     bs = len(mats) // max(num_layers, 1)
-    per_layer = sizes[:bs]
-    n = sum(per_layer)
-    b_host = torch.cat([torch.full((k,), i, dtype=torch.int64) for i, k in enumerate(per_layer)]) if n else torch.zeros(0, dtype=torch.int64)
-    o_host = torch.cat([torch.full((k,), offsets[i], dtype=torch.int64) for i, k in enumerate(per_layer)]) if n else torch.zeros(0, dtype=torch.int64)
-    both = torch.stack([b_host, o_host]).pin_memory().to(device, non_blocking=True)
-    out = []
+    # pair counts may differ between layers (min(Q_layer, K): encoder top-k count vs decoder queries): per-layer
+    # segments come from a cumulative sum of `sizes`, not from a uniform stride
+    b_parts, o_parts, bounds, off = [], [], [], 0
     for l in range(num_layers):
-        assert sizes[l * bs:(l + 1) * bs] == per_layer
-        seg = slice(l * n, (l + 1) * n)
-        out.append(MatchIndex(both[0], rows[seg], cols[seg] + both[1]))
-    return out
+        per_layer = sizes[l * bs:(l + 1) * bs]
+        n = sum(per_layer)
+        bounds.append((off, off + n))
+        off += n
+        for i, k in enumerate(per_layer):
+            b_parts.append(torch.full((k,), i, dtype=torch.int64))
+            o_parts.append(torch.full((k,), offsets[i], dtype=torch.int64))
+    if off:
+        both = torch.stack([torch.cat(b_parts), torch.cat(o_parts)])
+    else:
+        both = torch.zeros((2, 0), dtype=torch.int64)
+    both = both.pin_memory().to(device, non_blocking=True) if torch.device(device).type == "cuda" else both.to(device)
+    return [MatchIndex(both[0, a:b], rows[a:b], cols[a:b] + both[1, a:b]) for a, b in bounds]
 
 
 class ClassificationLoss(nn.Module):
@@ -159,16 +165,25 @@ class Det3DLoss(nn.Module):
     @staticmethod
     def normaliser(targets, device):
         """Mean number of GT boxes per rank, >= 1 (VD/losses.py:121-125): a host float in a single process, a 0-dim
-        device tensor (no host synchronisation) when the job is distributed over GPUs."""
-        n = float(sum(len(t["labels"]) for t in targets))
-        if _world_size() > 1:
-            t = torch.as_tensor([n], dtype=torch.float, device=device)
-            dist.all_reduce(t)
-            if t.is_cuda:
-                # stay on the device: a .item() here would drain the pipeline once per step on every rank
-                return (t / _world_size()).clamp_(min=1.0).reshape(())
-            n = float(t.item())
-        return max(n / _world_size(), 1.0)
+        device tensor (no host synchronisation) when the job is distributed over GPUs.  If the model requested the
+        all-reduce at the start of forward (``request_normaliser``) that result is used."""
+        pending = getattr(targets, "_num_boxes_async", None)
+        if pending is None:
+            pending = Det3DLoss.request_normaliser(targets, device)
+        return pending.result(floor=1.0)
+
+    @staticmethod
+    def request_normaliser(targets, device):
+        """Issue the 1-float all-reduce asynchronously; it depends only on the targets, so it can run under the whole
+        forward pass instead of blocking in the middle of the loss."""
+        from ...parallel import AsyncMean
+
+        pending = AsyncMean(float(sum(len(t["labels"]) for t in targets)), device)
+        try:
+            targets._num_boxes_async = pending
+        except AttributeError:  # a plain list: nothing to attach to
+            pass
+        return pending
 
     @staticmethod
     def layers_of(outputs):

@@ -166,6 +166,9 @@ class VoxelDETR(nn.Module):
 
     def forward(self, batched_inputs):
         targets = self.encode_targets(batched_inputs) if self.training else None
+        if targets is not None:
+            # the loss normaliser depends on the targets only: its all-reduce runs under the forward pass
+            self.transformer.proposal_head.losses.request_normaliser(targets, self.device)
         features, pos = self.extract(batched_inputs)
         hs, init_ref, inter_refs, memory, anchors, topk_idx = self.transformer(features, pos)
 

@@ -417,10 +417,30 @@ def colsum(x2d):
     return out
 
 
+# One sticky status word per device, OR-ed by the solver when a cost matrix is infeasible (non-finite entries).
+_LSA_STATUS = {}
+
+
+def lsa_status(device=None, clear=True):
+    """Synchronising check of the device Hungarian solver: raises ValueError — what scipy.optimize.linear_sum_assignment
+    raises for the reference (VD/modules/matcher.py:86-89) — if any cost matrix solved since the last check contained
+    non-finite entries.  Call it where the host synchronises anyway (loss read-back)."""
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    status = _LSA_STATUS.get(idx)
+    if status is None:
+        return
+    bad = int(status.item())
+    if bad and clear:
+        status.zero_()
+    if bad:
+        raise ValueError("matrix contains invalid numeric entries (device linear_sum_assignment)")
+
+
 def lsa_batched(mats):
     """Linear sum assignment of every cost matrix in ``mats`` (CUDA f32 [rows_k, cols_k], unit inner stride) on the
     device, scipy-identical.  Returns (rows int64 [sum n_k], cols int64 [sum n_k], sizes) with n_k = min(rows_k, cols_k);
-    problem k owns the slice [sum(sizes[:k]), sum(sizes[:k + 1])), pairs sorted by row.  No host synchronisation."""
+    problem k owns the slice [sum(sizes[:k]), sum(sizes[:k + 1])), pairs sorted by row.  No host synchronisation:
+    an infeasible problem (non-finite costs) still yields valid indices and is reported by lsa_status()."""
     if not mats:
         return None, None, []
     dev = mats[0].device
@@ -444,11 +464,14 @@ def lsa_batched(mats):
         n = min(r, c)
         sizes.append(n)
         off += n
-    out_rows = torch.empty((max(off, 1),), dtype=torch.int64, device=dev)
-    out_cols = torch.empty((max(off, 1),), dtype=torch.int64, device=dev)
+    out_rows = torch.zeros((max(off, 1),), dtype=torch.int64, device=dev)
+    out_cols = torch.zeros((max(off, 1),), dtype=torch.int64, device=dev)
+    status = _LSA_STATUS.get(dev.index)
+    if status is None:
+        status = _LSA_STATUS[dev.index] = torch.zeros(1, dtype=torch.int32, device=dev)
     t0 = PROFILER.begin() if PROFILER is not None else None
-    _lib.check(_lib.lib().efgb_lsa_batched(ptrs, rows, cols, lds, offs, count, _p(out_rows), _p(out_cols), _stream()),
-               "lsa_batched")
+    _lib.check(_lib.lib().efgb_lsa_batched_status(ptrs, rows, cols, lds, offs, count, _p(out_rows), _p(out_cols), _p(status),
+                                                  _stream()), "lsa_batched")
     if t0 is not None:
         PROFILER.end("lsa", t0, 4 * sum(m.numel() for m in mats) + 16 * off)
     return out_rows[:off], out_cols[:off], sizes

@@ -220,11 +220,18 @@ int efgb_dense_to_sparse(const float* dense, const int32_t* coords, int64_t num_
  *   problem k: cost matrix rows_host[k] x cols_host[k] f32 at device address cost_ptrs_host[k], row
  *   stride ld_host[k] floats; writes n_k = min(rows, cols) (row, col) pairs sorted by row to
  *   out_rows / out_cols + out_offsets_host[k] (device int64).  The *_host arrays are host memory and
- *   are consumed before the call returns.  Costs must be finite.
+ *   are consumed before the call returns.  Non-finite costs: see efgb_lsa_batched_status.
  * ------------------------------------------------------------------------------------------ */
 int efgb_lsa_batched(const void* const* cost_ptrs_host, const int32_t* rows_host,
                      const int32_t* cols_host, const int32_t* ld_host, const int64_t* out_offsets_host,
                      int count, int64_t* out_rows, int64_t* out_cols, efgb_stream_t stream);
+/* Same, with a device status word: bit 0 is OR-ed in when a problem is infeasible (non-finite costs — where scipy
+ * raises ValueError).  The pairs written for such a problem are still valid indices (free columns in ascending
+ * order), so nothing downstream reads out of bounds; the caller checks the word when it next synchronises. */
+int efgb_lsa_batched_status(const void* const* cost_ptrs_host, const int32_t* rows_host,
+                            const int32_t* cols_host, const int32_t* ld_host, const int64_t* out_offsets_host,
+                            int count, int64_t* out_rows, int64_t* out_cols, int32_t* status /* nullable */,
+                            efgb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused residual add + LayerNorm over the last dimension (nn.LayerNorm(d_model) applied to

@@ -1,5 +1,5 @@
-"""CPU, world_size 2 over gloo: the data-parallel plumbing (parameter broadcast, bucketed gradient
-averaging, the num_boxes all-reduce of the loss) reproduces single-process gradients."""
+"""CPU, world_size 2 over gloo: the data-parallel plumbing (parameter broadcast, gradient buckets reduced from inside
+backward, unused parameters, the asynchronous num_boxes all-reduce of the loss) reproduces single-process gradients."""
 import os
 import socket
 import sys
@@ -35,11 +35,17 @@ def _worker(rank, world, port, out_dir):
     avg = GradAverager(holder, bucket_bytes=256)  # tiny buckets -> several all-reduces
     avg.broadcast_parameters()
     torch.manual_seed(7)
-    data = torch.randn(2, 6, 8)
-    loss = model(data[rank]).square().mean()
-    loss.backward()
-    nbytes = avg.average_gradients()
-    assert nbytes == sum(p.numel() * 4 for p in model.parameters())
+    data = torch.randn(3, 2, 6, 8)
+    nbytes = 0
+    for it in range(3):  # step 0 learns which parameters receive gradients; steps 1-2 launch the buckets from the hooks
+        avg.zero_grad()
+        loss = model(data[it, rank]).square().mean()
+        loss.backward()
+        if it > 0:
+            assert any(b.launched for b in avg.buckets), "no bucket was reduced from inside backward"
+        nbytes = avg.finish()
+        avg.hide_unused()
+    assert nbytes == sum(p.numel() * 4 for p in holder.parameters())  # fixed-size buckets: independent of the data
     assert all(p.grad is None for p in unused.parameters())
     # loss normaliser: mean number of boxes per rank, all-reduced (VD/losses.py:121-125)
     targets = [{"labels": torch.zeros(3 + 4 * rank, dtype=torch.long)}]
@@ -67,7 +73,7 @@ def test_two_rank_gradient_average_matches_single_process(tmp_path):
         for p, q in zip(model.parameters(), r0["params"]):
             p.copy_(q)
     torch.manual_seed(7)
-    data = torch.randn(2, 6, 8)
+    data = torch.randn(3, 2, 6, 8)[2]  # the last of the three steps
     (0.5 * (model(data[0]).square().mean() + model(data[1]).square().mean())).backward()
     for p, g in zip(model.parameters(), r0["grads"]):
         assert torch.allclose(p.grad, g, atol=1e-6)

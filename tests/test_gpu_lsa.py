@@ -52,3 +52,30 @@ def test_lsa_strided_views_of_a_stacked_cost_tensor():
 def test_lsa_large_problem_falls_back_to_global_cost_reads():
     rng = np.random.default_rng(3)
     _check([rng.random((400, 300)).astype(np.float32)])  # 480 KB of costs: not staged in shared memory
+
+
+def test_lsa_non_finite_costs_yield_valid_indices_and_a_flag():
+    """scipy raises ValueError on NaN / infeasible matrices; the device solver cannot raise inside a kernel: it must
+    still write in-range, duplicate-free pairs (nothing downstream may gather out of bounds) and report through
+    ops.lsa_status(), which raises the same ValueError at the caller's next synchronisation point."""
+    from efg_b200 import ops
+
+    ops.lsa_status()  # clear
+    rng = np.random.default_rng(9)
+    good = torch.from_numpy(rng.random((20, 7)).astype(np.float32)).cuda()
+    bad = torch.from_numpy(rng.random((30, 9)).astype(np.float32)).cuda()
+    bad[:, 3] = float("nan")
+    inf = torch.full((6, 6), float("inf"), device="cuda")
+    rows, cols, sizes = ops.lsa_batched([good, bad, inf])
+    assert sizes == [7, 9, 6]
+    off = 0
+    for n, m in zip(sizes, (good, bad, inf)):
+        r, c = rows[off:off + n].cpu().numpy(), cols[off:off + n].cpu().numpy()
+        assert r.min() >= 0 and r.max() < m.shape[0] and c.min() >= 0 and c.max() < m.shape[1]
+        assert len(set(r.tolist())) == n and len(set(c.tolist())) == n
+        off += n
+    with pytest.raises(ValueError):
+        ops.lsa_status()
+    ops.lsa_status()  # cleared by the failed check
+    ops.lsa_batched([good])
+    ops.lsa_status()  # a clean solve leaves the flag down
