@@ -89,6 +89,8 @@ def _single_process_expected(use_cuda, mean_boxes):
 
     device = "cuda:0" if use_cuda else "cpu"
     sums = None
+    threads = torch.get_num_threads()
+    torch.set_num_threads(2)   # as in the workers: fp32 reductions depend on the thread count
     orig = Det3DLoss.normaliser
     Det3DLoss.normaliser = staticmethod(lambda targets, dev: max(mean_boxes, 1.0))
     try:
@@ -100,6 +102,7 @@ def _single_process_expected(use_cuda, mean_boxes):
             sums = g if sums is None else {n: sums[n] + g[n] for n in g}
     finally:
         Det3DLoss.normaliser = orig
+        torch.set_num_threads(threads)
     return {n: v / 2 for n, v in sums.items()}
 
 
