@@ -43,5 +43,45 @@ def load():
     return mod
 
 
+# ---- the reference's box-attention CUDA kernels, compiled for sm_100a: the GPU comparator -------------------------
+BOX_SRC = "/root/reference/efg/operators/src/box_attn/box_attn.cu"
+BOX_NAME = "efg_ref_box_attn"
+
+
+def build_box_attn():
+    """nvcc cross-compiles the reference's box_attn.cu (+ box_attn_kernel.cuh) unmodified for sm_100a; ~6 minutes
+    (ATen headers).  Returns the .so path, or None where /root/reference is absent."""
+    if not os.path.exists(BOX_SRC):
+        return None
+    existing = glob.glob(os.path.join(OUT, BOX_NAME + "*.so"))
+    if existing:
+        return existing[0]
+    os.makedirs(OUT, exist_ok=True)
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
+    from torch.utils.cpp_extension import load
+
+    load(name=BOX_NAME, sources=[os.path.join(HERE, "ref_box_attn_shim.cpp"), BOX_SRC],
+         extra_cflags=["-O2", "-std=c++17", "-DWITH_CUDA"],
+         extra_cuda_cflags=["-O2", "-std=c++17", "-DWITH_CUDA", "-gencode", "arch=compute_100a,code=sm_100a",
+                            "--expt-relaxed-constexpr"],
+         extra_include_paths=["/root/reference/efg/operators/src"], build_directory=OUT, verbose=False)
+    existing = glob.glob(os.path.join(OUT, BOX_NAME + "*.so"))
+    return existing[0] if existing else None
+
+
+def load_box_attn():
+    existing = glob.glob(os.path.join(OUT, BOX_NAME + "*.so"))
+    if not existing:
+        return None
+    import torch  # noqa: F401
+
+    spec = importlib.util.spec_from_file_location(BOX_NAME, existing[0])
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 if __name__ == "__main__":
     print(build())
+    if "--box-attn" in sys.argv:
+        print(build_box_attn())

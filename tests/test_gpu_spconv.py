@@ -132,7 +132,8 @@ def test_config1_subm16_on_20k_cloud():
     nbr = sc.subm_rulebook(np.pad(oc, ((0, 0), (1, 0))), 1, [41, 1504, 1504], 3)
     exp = sc.conv(feats, conv.weight.detach(), None, nbr)
     y = conv.cuda()(SparseConvTensor(feats.cuda(), coords, [41, 1504, 1504], 1))
-    assert (y.features.cpu() - exp).abs().max().item() < 1e-5
+    # default precision bf16x3: measured 1.3e-5 on outputs of magnitude ~0.5 (the bar is north_star's 1e-3)
+    assert (y.features.cpu() - exp).abs().max().item() < 1e-4
 
 
 def test_dense_roundtrip_and_grad():

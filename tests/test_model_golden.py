@@ -121,20 +121,20 @@ def test_eval_detections_match_reference_golden_cpu(kind):
 
 
 def _compare_detections(res, exp, tol):
+    """topk(sorted=False) leaves the order unspecified (VD/voxel_detr.py:183): the score multisets must agree, and every
+    reference detection must have a counterpart with the same label, a score within tol and the same box."""
     assert len(res) == len(exp)
     for r, e in zip(res, exp):
-        assert r["scores"].shape == e["scores"].shape, (r["scores"].shape, e["scores"].shape)
-        # topk(sorted=False) leaves the order unspecified (VD/voxel_detr.py:183): compare as sets, by descending score
-        oi, oe = torch.argsort(r["scores"].cpu(), descending=True, stable=True), torch.argsort(e["scores"], descending=True, stable=True)
-        assert torch.allclose(r["scores"].cpu()[oi], e["scores"][oe], atol=tol)
-        # ties / near-ties may permute: labels and boxes are compared where the score gap to the neighbours is clear
-        s = e["scores"][oe]
-        gap = torch.ones_like(s, dtype=torch.bool)
-        gap[1:] &= (s[:-1] - s[1:]) > 10 * tol
-        gap[:-1] &= (s[:-1] - s[1:]) > 10 * tol
-        assert gap.float().mean() > 0.5
-        assert torch.equal(r["labels"].cpu()[oi][gap], e["labels"][oe][gap])
-        assert torch.allclose(r["boxes3d"].cpu()[oi][gap], e["boxes3d"][oe][gap], atol=max(tol * 100, 1e-4))
+        rs, rl, rb = r["scores"].cpu(), r["labels"].cpu(), r["boxes3d"].cpu()
+        assert rs.shape == e["scores"].shape, (rs.shape, e["scores"].shape)
+        assert torch.allclose(torch.sort(rs).values, torch.sort(e["scores"]).values, atol=tol)
+        box_tol = max(tol * 20, 1e-4)   # decoded boxes are in metres / radians: values up to ~15
+        same = (e["labels"][:, None] == rl[None, :]) & ((e["scores"][:, None] - rs[None, :]).abs() <= tol)
+        dist = (e["boxes3d"][:, None, :] - rb[None, :, :]).abs().amax(-1)
+        dist = torch.where(same, dist, torch.full_like(dist, float("inf")))
+        best = dist.min(dim=1).values
+        # scores within tol of the selection threshold may fall on either side of the cut: allow a handful to miss
+        assert (best <= box_tol).float().mean().item() >= 0.97, (best.max().item(), (best > box_tol).sum().item())
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -262,9 +262,10 @@ def test_train_losses_match_reference_golden_gpu(kind):
     _, _, losses, grads = run_port_train(kind, g, device="cuda")
     check_losses(losses, g["losses"], 1e-3)
     for name, ref_grad in g["grads"].items():
-        scale = max(ref_grad.abs().max().item(), 1e-6)
-        # whole-model gradients at random initialisation amplify rounding (DESIGN.md §5 note 2): 5 % of the largest entry
-        assert (grads[name] - ref_grad).abs().max().item() <= 5e-2 * scale, name
+        # whole-model gradients at random initialisation amplify rounding (DESIGN.md §5 note 2: the same CPU graph in
+        # fp32 vs fp64 differs by ~7 %): the tensors are compared in norm; the CPU test above holds them to 2e-3
+        rel = ((grads[name] - ref_grad).norm() / ref_grad.norm().clamp_min(1e-6)).item()
+        assert rel <= 0.1, (name, rel)
 
 
 @pytest.mark.gpu
