@@ -111,10 +111,16 @@ def hard_voxelize_batched(points, scene_offsets, voxel_size, coors_range, max_po
     counts = torch.empty((batch + 1,), dtype=torch.int32, device=dev)
     wsb = L.efgb_voxelize_workspace_bytes(n, batch)
     ws = workspace(wsb, dev)
+    t0 = PROFILER.begin() if PROFILER is not None else None
     rc = L.efgb_hard_voxelize(_p(points), n, f, _p(scene_offsets), batch, _lib.f32array(voxel_size),
                               _lib.f32array(coors_range), int(max_points), int(max_voxels), _p(voxels), _p(coors),
                               int(coors_dim), _p(npv), _p(mean), _p(counts), _p(ws), ws.numel(), _stream())
     _lib.check(rc, "hard_voxelize")
+    if t0 is not None:
+        # algorithmic bytes: points in; per voxel mean feats + coords + count out, with M ~ N / 2 unknown
+        # on the host here (no sync): the calibrated ratio M = 0.5 N of the survey's real frame is used
+        m_est = n // 2
+        PROFILER.end("voxelize", t0, 4 * (n * f + m_est * (f + coors_dim + 1) + (m_est * max_points * f if want_voxels else 0)))
     return {"voxels": voxels, "coors": coors, "num_points_per_voxel": npv, "mean": mean, "counts": counts}
 
 
@@ -201,9 +207,12 @@ def subm_rulebook(coords, batch, grid_dhw, ksize, rows_sorted=False):
     if wsb == 0:
         raise RuntimeError("batch*D*H*W = %r does not fit the 32-bit cell id" % ((batch, *grid_dhw),))
     ws = workspace(wsb, dev)
+    t0 = PROFILER.begin() if PROFILER is not None else None
     rc = L.efgb_subm_rulebook(_p(coords), m, int(batch), dhw, _lib.i32x3(k), 1 if rows_sorted else 0, _p(nbr), _p(ws),
                               ws.numel(), _stream())
     _lib.check(rc, "subm_rulebook")
+    if t0 is not None:
+        PROFILER.end("rulebook_subm", t0, m * 16 + m * taps * 4)   # coords in, neighbour table out
     return nbr
 
 
@@ -231,6 +240,7 @@ def sparse_rulebook(coords, batch, in_dhw, ksize, stride, padding):
     out_dhw = _lib.i32x3([0, 0, 0])
     m_dev = torch.zeros((1,), dtype=torch.int32, device=dev)
     args = (_p(coords), m_in, int(batch), _lib.i32x3(in_dhw), _lib.i32x3(k), _lib.i32x3(s), _lib.i32x3(p))
+    t0 = PROFILER.begin() if PROFILER is not None else None
     _lib.check(L.efgb_sparse_rulebook_phase1(*args, out_dhw, _p(m_dev), _p(ws), ws.numel(), _stream()),
                "sparse_rulebook_phase1")
     m_out = int(m_dev.item())  # the one host sync of a strided conv
@@ -239,6 +249,8 @@ def sparse_rulebook(coords, batch, in_dhw, ksize, stride, padding):
     nbr_t = torch.empty((m_in, taps), dtype=torch.int32, device=dev)
     _lib.check(L.efgb_sparse_rulebook_phase2(*args, m_out, _p(out_coords), _p(nbr), _p(nbr_t), _p(ws), ws.numel(),
                                              _stream()), "sparse_rulebook_phase2")
+    if t0 is not None:  # includes the host round trip for the output count
+        PROFILER.end("rulebook_sparse", t0, m_in * 16 + m_out * 16 + (m_out + m_in) * taps * 4)
     return out_coords, [int(out_dhw[0]), int(out_dhw[1]), int(out_dhw[2])], nbr, nbr_t
 
 
@@ -633,8 +645,11 @@ def sparse_to_dense(feats, coords, batch, grid_dhw):
     d, h, w = [int(x) for x in grid_dhw]
     dense = torch.empty((batch, c, d, h, w), dtype=torch.float32, device=feats.device)
     L = _lib.lib()
+    t0 = PROFILER.begin() if PROFILER is not None else None
     rc = L.efgb_sparse_to_dense(_p(feats), _p(coords), m, c, int(batch), _lib.i32x3(grid_dhw), _p(dense), _stream())
     _lib.check(rc, "sparse_to_dense")
+    if t0 is not None:
+        PROFILER.end("sparse_to_dense", t0, 4 * (feats.numel() + dense.numel()) + coords.numel() * 4)
     return dense
 
 
@@ -824,3 +839,42 @@ class BoxProjGridSoftmaxFunction(torch.autograd.Function):
         if t0 is not None:
             PROFILER.end("box_grid_softmax_bwd", t0, 4 * (2 * b * lq * (n_attn + n_box) + g_attn.numel() + g_loc.numel()))
         return g_proj, None, None, None, None, None
+
+
+# --------------------------------------------------------------------------------------------
+# NVTX ranges (tracing): one range per operator call, named efgb::<op>
+# --------------------------------------------------------------------------------------------
+_NVTX_OPS = ("hard_voxelize_batched", "dynamic_voxelize", "dynamic_scatter_forward", "dynamic_scatter_backward",
+             "subm_rulebook", "sparse_rulebook", "spconv_forward", "spconv_tc", "spconv_tc_wgrad", "spconv_wgrad",
+             "split_bf16", "packed_weights", "colsum", "lsa_batched", "sparse_to_dense", "dense_to_sparse",
+             "box_attn_forward", "box_attn_backward", "dense_linear", "fused_ffn", "add_layer_norm")
+_nvtx_on = False
+
+
+def enable_nvtx():
+    """Wrap every operator of this module in an NVTX range (torch.cuda.nvtx), so an nsys / ncu --nvtx timeline shows
+    the operator each kernel belongs to.  Off by default (a push / pop pair costs ~1 us per operator); bench.py
+    --profile-step turns it on.  Callers that imported a function by name before this call keep the unwrapped one."""
+    global _nvtx_on
+    if _nvtx_on:
+        return
+    import functools
+
+    g = globals()
+    for name in _NVTX_OPS:
+        fn = g.get(name)
+        if fn is None:
+            continue
+
+        def wrap(fn=fn, label="efgb::" + name):
+            @functools.wraps(fn)
+            def inner(*a, **k):
+                torch.cuda.nvtx.range_push(label)
+                try:
+                    return fn(*a, **k)
+                finally:
+                    torch.cuda.nvtx.range_pop()
+            return inner
+
+        g[name] = wrap()
+    _nvtx_on = True
