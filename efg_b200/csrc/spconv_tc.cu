@@ -929,7 +929,7 @@ __device__ __forceinline__ void wgrad_produce(const WgradParams& p, const int st
   constexpr int kGroupThreads = kWarpsPerGroup * 32;
   constexpr int kPiecesA = (kWgRows * 32) / kGroupThreads;  // 16-byte pieces of the A tile per thread
   constexpr int kRowStepA = kGroupThreads / 32;             // rows between consecutive A pieces of a thread
-  constexpr int kBatch = 8;                                  // grad_out pieces per thread per batch
+  constexpr int kBatch = 4;                                  // grad_out pieces per thread per batch (8 spilled: 80-register cap)
   const int gidx = warp / kWarpsPerGroup;
   const int tg = (warp % kWarpsPerGroup) * 32 + lane;
   const int pg = p.n_pad / 4;  // 16-byte pieces per grad_out row slab (padded)
@@ -946,10 +946,10 @@ __device__ __forceinline__ void wgrad_produce(const WgradParams& p, const int st
 
   // A pieces of this thread: column piece pcA (fixed), rows rA0 + i * kRowStepA
   const int pcA = tg & 31, rA0 = tg >> 5;
-  uint32_t offA[kPiecesA];
-#pragma unroll
-  for (int i = 0; i < kPiecesA; ++i)
-    offA[i] = static_cast<uint32_t>(pcA >> 3) * (kWgRows * 128) + mn_piece_offset(rA0 + i * kRowStepA, pcA);
+  // rows advance by kRowStepA (a multiple of 4) between a thread's pieces, so the swizzle term (r & 3) is constant:
+  // piece i sits kRowStepA * 128 bytes after piece i - 1 (no per-piece offset array: registers are the budget here)
+  static_assert(kRowStepA % 4 == 0, "constant swizzle phase per thread");
+  const uint32_t offA0 = static_cast<uint32_t>(pcA >> 3) * (kWgRows * 128) + mn_piece_offset(rA0, pcA);
   // grad_out pieces (fast path): column piece pcG (fixed), rows rG0 + j * rows_per_pass
   const int pcG = g_fast ? (tg & (pg - 1)) : 0;
   const int rG0 = g_fast ? (tg >> pg_shift) : 0;
@@ -1032,7 +1032,7 @@ __device__ __forceinline__ void wgrad_produce(const WgradParams& p, const int st
     uint8_t* g_hi = a_hi + kParts * a_part;
     uint8_t* g_lo = g_hi + g_part;
 #pragma unroll
-    for (int i = 0; i < kPiecesA; ++i) split_store(a_hi, a_lo, offA[i], va[i], kSplit);
+    for (int i = 0; i < kPiecesA; ++i) split_store(a_hi, a_lo, offA0 + static_cast<uint32_t>(i * kRowStepA * 128), va[i], kSplit);
     for (int e0 = 0; e0 < g_total; e0 += kGroupThreads * kBatch) {
       if (e0 > 0) load_g(e0);
       if (g_fast) {
@@ -1115,63 +1115,66 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_wgrad_tc_kernel(const Wgra
     else
       wgrad_produce<kSplit, 2>(p, stages, smem, stage_bytes, a_part, g_part, full_bar, empty_bar, warp, lane);
   } else if (warp == kMmaWarp) {
-    if (lane == 0) {
+    // the whole warp runs the loop convergently and one elected lane issues (see spconv_tc_kernel's MMA issuer:
+    // uniform-register operands instead of ~100 cycles of R2UR moves per tcgen05.mma)
+    {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
-      uint32_t acc_phase[2] = {0, 0};
+      uint32_t acc_phases = 0;   // bit a = phase of accumulator a (no dynamically indexed local array: that was a stack frame)
       // both operands MN-major: bits 15 and 16
       const uint32_t idesc = make_idesc_tf32(kTileM, p.n_pad) | (1u << 15) | (1u << 16);
       const uint32_t blk = kWgRows * 128;  // column-block stride
+      const uint32_t smem_u = smem_u32(smem);
+      const uint32_t full_u = smem_u32(full_bar), empty_u = smem_u32(empty_bar);
+      const int stages_per_item = static_cast<int>(p.rows_per_chunk / kWgRows);
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        const int64_t row_begin = static_cast<int64_t>(item / p.groups) * p.rows_per_chunk;
-        int64_t row_end = row_begin + p.rows_per_chunk;
-        if (row_end > p.num_out) row_end = p.num_out;
-        mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase[acc] ^ 1);
+        mbar_wait(smem_u32(&tmem_empty[acc]), ((acc_phases >> acc) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * p.n_pad);
-        uint32_t first = 1;
-        (void)row_end;
-        for (int64_t rb = row_begin; rb < row_begin + p.rows_per_chunk; rb += kWgRows) {
-          mbar_wait(smem_u32(&full_bar[stage]), phase);
+        for (int st = 0; st < stages_per_item; ++st) {
+          mbar_wait(full_u + stage * 8, phase);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t a_hi = smem_u + static_cast<uint32_t>(stage * stage_bytes);
           const uint32_t a_lo = a_hi + a_part;
           const uint32_t g_hi = a_hi + kParts * a_part;
           const uint32_t g_lo = g_hi + g_part;
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < kWgRows / 8; ++ks) {
-            const uint32_t o = ks * 1024;  // 8 rows x 128 B inside every column block
-            if (kSplit) {
-              tc_mma_tf32(tmem_d, make_desc_mn_sw128(a_lo + o, blk), make_desc_mn_sw128(g_hi + o, blk), idesc, first ? 0u : 1u);
-              tc_mma_tf32(tmem_d, make_desc_mn_sw128(a_hi + o, blk), make_desc_mn_sw128(g_lo + o, blk), idesc, 1u);
-              tc_mma_tf32(tmem_d, make_desc_mn_sw128(a_hi + o, blk), make_desc_mn_sw128(g_hi + o, blk), idesc, 1u);
-            } else {
-              tc_mma_tf32(tmem_d, make_desc_mn_sw128(a_hi + o, blk), make_desc_mn_sw128(g_hi + o, blk), idesc, first ? 0u : 1u);
+            for (int ks = 0; ks < kWgRows / 8; ++ks) {
+              const uint32_t o = ks * 1024;  // 8 rows x 128 B inside every column block
+              const uint32_t accum = (st | ks) ? 1u : 0u;
+              if (kSplit) {
+                tc_mma_tf32(tmem_d, make_desc_mn_sw128(a_lo + o, blk), make_desc_mn_sw128(g_hi + o, blk), idesc, accum);
+                tc_mma_tf32(tmem_d, make_desc_mn_sw128(a_hi + o, blk), make_desc_mn_sw128(g_lo + o, blk), idesc, 1u);
+                tc_mma_tf32(tmem_d, make_desc_mn_sw128(a_hi + o, blk), make_desc_mn_sw128(g_hi + o, blk), idesc, 1u);
+              } else {
+                tc_mma_tf32(tmem_d, make_desc_mn_sw128(a_hi + o, blk), make_desc_mn_sw128(g_hi + o, blk), idesc, accum);
+              }
             }
-            first = 0;
+            tc_commit(empty_u + stage * 8);
           }
-          tc_commit(smem_u32(&empty_bar[stage]));
+          __syncwarp();
           if (++stage == stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        tc_commit(smem_u32(&tmem_full[acc]));
-        acc_phase[acc] ^= 1;
+        if (elect_one()) tc_commit(smem_u32(&tmem_full[acc]));
+        __syncwarp();
+        acc_phases ^= 1u << acc;
         acc ^= 1;
       }
     }
-    __syncwarp();
   } else if (warp >= kLoaderWarp + 1) {
     // ================= epilogue: TMEM -> red.global.add into dW[co][tap][ci] =================
     const int quarter = warp & 3;
     int acc = 0;
-    uint32_t acc_phase[2] = {0, 0};
+    uint32_t acc_phases = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int g = item % p.groups;
       const int64_t row_begin = static_cast<int64_t>(item / p.groups) * p.rows_per_chunk;
-      mbar_wait(smem_u32(&tmem_full[acc]), acc_phase[acc]);
+      mbar_wait(smem_u32(&tmem_full[acc]), (acc_phases >> acc) & 1u);
       tc_fence_after();
       const int flat = g * 128 + quarter * 32 + lane;
       const int tap = flat / p.c_in;
@@ -1194,7 +1197,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_wgrad_tc_kernel(const Wgra
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
-      acc_phase[acc] ^= 1;
+      acc_phases ^= 1u << acc;
       acc ^= 1;
     }
   }
