@@ -60,6 +60,8 @@ def parse_args():
     ap.add_argument("--points", type=int, default=None)
     ap.add_argument("--scenes", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="keep the static section (FPN top-down, transformer, heads) eager instead of CUDA-graphed")
     ap.add_argument("--cpu-points", type=int, default=POINTS_PER_SCENE)
     ap.add_argument("--profile-step", action="store_true",
                     help="for `ncu --profile-from-start off`: after the warm-up run ONE step between "
@@ -307,6 +309,11 @@ def run_efgb200(args, backend=None):
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # The whole job runs on one non-default stream.  CUDA-graph capture of the static section needs it: autograd ties a
+    # parameter's gradient accumulator to the stream the parameter was first used on, and a capture may fork / join
+    # any stream except the legacy default one ("operation would make the legacy stream depend on a capturing blocking
+    # stream").  Every event below is recorded on this stream.
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
     torch.manual_seed(0)
     if args.workload == "config1":
         return run_config1(args, dev)
@@ -376,6 +383,21 @@ def run_efgb200(args, backend=None):
         step(resident[i % n_batches])
     barrier()
 
+    # CUDA graphs for the static-shape section of the step (FPN top-down, encoder, decoder, heads; forward + backward)
+    graph_state = "none"
+    if backend is None and not args.no_graph and not args.profile_step and hasattr(model, "enable_static_graph"):
+        if args.workload == "voxel_detr":
+            ok = model.enable_static_graph([({"points": p}, {"annotations": a}) for p, a in resident[0]])
+            graph_state = "static section (FPN top-down + transformer + heads), forward and backward" if ok else \
+                "none (capture failed: %s)" % model.static_graph_error
+            if not ok:
+                sys.stderr.write("bench.py: CUDA graph capture failed, running eagerly: %s\n" % model.static_graph_error)
+            for i in range(3):
+                step(resident[i % n_batches])
+            barrier()
+        else:
+            graph_state = "none (the denoising queries make the decoder length data-dependent)"
+
     if args.profile_step:
         ops.enable_nvtx()
         torch.cuda.profiler.start()
@@ -395,7 +417,11 @@ def run_efgb200(args, backend=None):
     value = scenes_total / (ms_dev / 1e3)
     e2e_value = scenes_total / (ms_e2e / 1e3)
 
-    # in-situ kernel attribution (extra steps, CUDA events around each library launch)
+    # in-situ kernel attribution (extra steps, CUDA events around each library launch); eager: a graph replay runs no
+    # Python, so the per-launch events could not be recorded inside it
+    graphed_call = getattr(model, "_static_call", None)
+    if graphed_call is not None:
+        model._static_call = None
     ops.PROFILER = ops.KernelProfiler()
     prof_steps = 2
     t_prof0 = torch.cuda.Event(enable_timing=True)
@@ -431,7 +457,7 @@ def run_efgb200(args, backend=None):
                    "num_queries": NUM_QUERIES if args.workload in ("voxel_detr", "conquer") else None,
                    "grid": "x".join(str(int(g)) for g in spec.grid_size), "step": "voxelize+fwd+bwd+allreduce+adamw",
                    "conv_precision": ops.CONV_PRECISION if backend is None else "fp32 torch ops",
-                   "cuda_graph": "none", "parallelism": "dp%d" % world,
+                   "cuda_graph": graph_state, "parallelism": "dp%d" % world,
                    "l2": "flushed before every timed step (256 MiB memset, inside the timed span)"},
         "e2e": {"value": round(e2e_value, 3), "unit": "scenes/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": last_loss},

@@ -40,6 +40,40 @@ class Backbone3d(nn.Module):
         return [(feats[f], self.position_encoding(feats[f]).type_as(feats[f])) for f in self.out_features]
 
 
+class _StaticSection(nn.Module):
+    """Everything between the sparse backbone and the losses: FPN top-down convs -> input projection -> position
+    encoding -> box-attention encoder -> top-k proposals -> decoder -> detection heads.  All of its shapes are fixed by
+    the BEV grid, the batch size and num_queries, so forward AND backward can be held in CUDA graphs
+    (``VoxelDETR.enable_static_graph``): ~1000 kernel launches of a launch-bound step become two graph launches.
+    Not registered as a sub-module of the detector (its members already are): the state_dict is unchanged."""
+
+    def __init__(self, det, feat_names):
+        super().__init__()
+        ext = det.backbone.extractor
+        self.det = [det]
+        self.feat_names = list(feat_names)
+        self.lateral_convs = nn.ModuleList(ext.lateral_convs)
+        self.output_convs = nn.ModuleList(ext.output_convs)
+        self.input_proj = det.input_proj
+        self.transformer = det.transformer
+
+    def forward(self, *maps):
+        det = self.det[0]
+        feats = det.backbone.extractor.forward_dense(dict(zip(self.feat_names, maps)))
+        feats_pos = [(feats[f], det.backbone.position_encoding(feats[f]).type_as(feats[f])) for f in det.backbone.out_features]
+        features = [det.input_proj[i](fp[0]) for i, fp in enumerate(feats_pos)]
+        hs, init_ref, inter_refs, memory, anchors, topk_idx = det.transformer(features, [fp[1] for fp in feats_pos])
+        head = det.transformer.decoder.detection_head
+        cls_out, box_out = [], []
+        for i in range(hs.shape[0]):
+            c, b = head(hs[i], init_ref if i == 0 else inter_refs[i - 1], i)
+            cls_out.append(c)
+            box_out.append(b)
+        enc_cls, enc_box = det.transformer._enc_head_out
+        det.transformer._enc_head_out = None
+        return torch.stack(cls_out), torch.stack(box_out), memory, anchors, topk_idx, enc_cls, enc_box
+
+
 def collate_voxels(samples, device):
     """The voxel part of waymo.py:143-183: concatenate per-scene arrays, prepend the batch index."""
     voxels = torch.from_numpy(np.concatenate([s["voxels"] for s in samples], 0)).to(device)
@@ -164,11 +198,52 @@ class VoxelDETR(nn.Module):
         features = [self.input_proj[i](fp[0]) for i, fp in enumerate(feats_pos)]
         return features, [fp[1] for fp in feats_pos]
 
+    # ---------------------------------------------------------------------------------------
+    def bottom_up_maps(self, batched_inputs):
+        """Voxelize + sparse backbone: the dense bottom-up feature maps the FPN needs (dynamic shapes end here)."""
+        batch_size = len(batched_inputs)
+        samples = [bi[0] for bi in batched_inputs]
+        if "voxels" in samples[0]:
+            voxels, coords, npv, input_shape = collate_voxels(samples, self.device)
+        else:
+            voxels, coords, npv, input_shape = self.voxelize_on_device(samples)
+        encoded = self.backbone.reader(voxels, npv, coords)
+        return self.backbone.extractor.bottom_up(encoded, coords, batch_size, input_shape)
+
+    def enable_static_graph(self, batched_inputs):
+        """Capture the static section (see _StaticSection) into CUDA graphs, forward and backward
+        (torch.cuda.make_graphed_callables), using `batched_inputs` as the sample.  Training mode, fixed batch size.
+        Returns True on success; on failure the model keeps running eagerly and the reason is kept in
+        ``self.static_graph_error`` (never silent: bench.py reports it)."""
+        self.static_graph_error = None
+        try:
+            if not (self.training and self.device.type == "cuda" and self.reuse_proposal_head):
+                raise RuntimeError("needs a CUDA model in training mode with reuse_proposal_head")
+            feats = self.bottom_up_maps(batched_inputs)
+            names = [n for n in self.backbone.extractor.in_features if n in feats]
+            section = _StaticSection(self, names)
+            sample = tuple(feats[n].detach().clone().requires_grad_(True) for n in names)
+            torch.cuda.synchronize()
+            self._static_call = torch.cuda.make_graphed_callables(section, sample, allow_unused_input=True)
+            self._static_names, self._static_batch = names, len(batched_inputs)
+            self._static_section = [section]
+            return True
+        except Exception as e:  # noqa: BLE001 — capture failures are reported, the eager path stays intact
+            self._static_call = None
+            self.static_graph_error = "%s: %s" % (type(e).__name__, e)
+            return False
+
     def forward(self, batched_inputs):
         targets = self.encode_targets(batched_inputs) if self.training else None
         if targets is not None:
             # the loss normaliser depends on the targets only: its all-reduce runs under the forward pass
             self.transformer.proposal_head.losses.request_normaliser(targets, self.device)
+        call = getattr(self, "_static_call", None)
+        if call is not None and self.training and torch.is_grad_enabled() and len(batched_inputs) == self._static_batch:
+            feats = self.bottom_up_maps(batched_inputs)
+            cls_out, box_out, memory, anchors, topk_idx, enc_cls, enc_box = call(*[feats[n] for n in self._static_names])
+            self.transformer._enc_head_out = (enc_cls, enc_box)
+            return self.losses(cls_out, box_out, memory, anchors, topk_idx, targets)
         features, pos = self.extract(batched_inputs)
         hs, init_ref, inter_refs, memory, anchors, topk_idx = self.transformer(features, pos)
 

@@ -95,7 +95,10 @@ class FPN(nn.Module):
             self.bottom_up.compute_features = feats
 
     def forward(self, *args, **kwargs):
-        feats = self.bottom_up(*args, **kwargs)
+        return self.forward_dense(self.bottom_up(*args, **kwargs), (args, kwargs))
+
+    def forward_dense(self, feats, bottom_up_call=None):
+        """The dense top-down part on the bottom-up feature maps (static shapes: the part a CUDA graph can hold)."""
         if self.needed is None:
             return self._forward_all(feats)
         top_down_stages = self._stages[::-1]
@@ -117,6 +120,9 @@ class FPN(nn.Module):
                 results["p%d" % st] = output(prev)
         missing = wanted - set(results)
         if missing:  # a top-block level was requested: fall back to the full computation
+            if bottom_up_call is None:
+                raise RuntimeError("FPN.forward_dense: level(s) %r need the full bottom-up pass" % sorted(missing))
+            args, kwargs = bottom_up_call
             return {k: v for k, v in self._forward_all(self.bottom_up(*args, **kwargs)).items() if k in wanted}
         return results
 

@@ -368,14 +368,17 @@ def packed_weights(w_param, mode, split):
     key = (w_param.data_ptr(), tuple(w_param.shape), mode, split, w_param.device.index)
     ver = base._version
     hit = _PACK_CACHE.get(key)
-    if hit is not None and hit[0] == ver and hit[2]() is base:   # same tensor object, not updated in place since
-        return hit[1]
+    capturing = torch.cuda.is_current_stream_capturing()
+    if hit is not None and hit[0] == ver and hit[2]() is base and not capturing:   # same tensor object, not updated since
+        return hit[1]   # (under stream capture the pack kernel must be part of the graph: replays read the live weights)
     L = _lib.lib()
     packed = torch.empty(L.efgb_spconv_tc_packed_bytes(taps, c_red, n_out, split) // 4, dtype=torch.float32, device=w_param.device)
     t0 = PROFILER.begin() if PROFILER is not None else None
     _lib.check(L.efgb_spconv_tc_pack(_p(w_param), c_out, taps, c_in, mode, split, _p(packed), _stream()), "spconv_tc_pack")
     if t0 is not None:
         PROFILER.end("spconv_pack_weights", t0, 4 * (w_param.numel() + packed.numel()))
+    if capturing:
+        return packed   # lives in the graph's memory pool; never handed to eager callers
     if len(_PACK_CACHE) >= _PACK_CACHE_MAX:
         _PACK_CACHE.clear()
     _PACK_CACHE[key] = (ver, packed, weakref.ref(base))
