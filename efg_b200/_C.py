@@ -85,3 +85,48 @@ def box_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, at
     _check_im2col(value.shape[0], im2col_step)
     return list(ops.box_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
                                       grad_output))
+
+
+# ---- BEV IoU / rotated NMS (vision.cpp:100-104, iou3d_nms.cpp:22-178) ---------------------------------------------
+def _check_boxes(t, name):
+    # CHECK_INPUT of the reference: CUDA + contiguous (iou3d_nms.cpp:11-13)
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDAtensor " % name)
+    if not t.is_contiguous():
+        raise RuntimeError("%s must be contiguous " % name)
+
+
+def boxes_overlap_bev_gpu(boxes_a, boxes_b, ans_overlap):
+    """iou3d_nms.cpp:22-40: fills ans_overlap [N, M] with the BEV overlap areas; returns 1."""
+    for t, n in ((boxes_a, "boxes_a"), (boxes_b, "boxes_b"), (ans_overlap, "ans_overlap")):
+        _check_boxes(t, n)
+    ans_overlap.copy_(ops.boxes_bev(boxes_a.float(), boxes_b.float(), overlap=True))
+    return 1
+
+
+def boxes_iou_bev_gpu(boxes_a, boxes_b, ans_iou):
+    """iou3d_nms.cpp:42-58: fills ans_iou [N, M] with the BEV IoU of rotated boxes; returns 1."""
+    for t, n in ((boxes_a, "boxes_a"), (boxes_b, "boxes_b"), (ans_iou, "ans_iou")):
+        _check_boxes(t, n)
+    ans_iou.copy_(ops.boxes_bev(boxes_a.float(), boxes_b.float(), overlap=False))
+    return 1
+
+
+def _nms(boxes, keep, thresh, normal):
+    _check_boxes(boxes, "boxes")
+    if not keep.is_contiguous():
+        raise RuntimeError("keep must be contiguous ")
+    kept, count = ops.nms_bev(boxes, thresh, normal=normal)
+    n = int(count.item())                    # the reference's signature returns a host int
+    keep[:n].copy_(kept[:n])                 # `keep` is a host LongTensor in the reference (iou3d_nms.py:113)
+    return n
+
+
+def nms_gpu(boxes, keep, nms_overlap_thresh):
+    """iou3d_nms.cpp:60-121: boxes [N,7] sorted by score; writes the kept indices into `keep`, returns their number."""
+    return _nms(boxes, keep, nms_overlap_thresh, False)
+
+
+def nms_normal_gpu(boxes, keep, nms_overlap_thresh):
+    """iou3d_nms.cpp:124-176: the same with axis-aligned IoU (heading ignored)."""
+    return _nms(boxes, keep, nms_overlap_thresh, True)

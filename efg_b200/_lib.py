@@ -52,6 +52,10 @@ SIGNATURES = {
     "efgb_spconv_wgrad": (_int, [_vp, _i64, _int, _vp, _vp, _i64, _int, _int, _vp, _vp]),
     "efgb_sparse_to_dense": (_int, [_vp, _vp, _i64, _int, _int, _host_i32x3, _vp, _vp]),
     "efgb_dense_to_sparse": (_int, [_vp, _vp, _i64, _int, _int, _host_i32x3, _vp, _vp]),
+    "efgb_boxes_bev_workspace_bytes": (_sz, [_i64, _i64]),
+    "efgb_boxes_bev": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _vp, _sz, _vp]),
+    "efgb_nms_bev_workspace_bytes": (_sz, [_i64]),
+    "efgb_nms_bev": (_int, [_vp, _i64, ctypes.c_float, _int, _vp, _vp, _vp, _sz, _vp]),
     "efgb_lsa_batched": (_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
                                 ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64), _int, _vp, _vp, _vp]),
     "efgb_lsa_batched_status": (_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),

@@ -76,6 +76,7 @@ class CenterHead(nn.Module):
         self.criterion = FastFocalLoss()
         self.criterion_reg = RegLoss()
         self.box_n_dim = 9 if "vel" in self.common_heads else 7
+        self.rotate_nms = None  # set by the detector from its backend; None = the CUDA operator
         norm = config.model.neck.norm
         self.shared_conv = nn.Sequential(
             nn.Conv2d(self.in_channels, share_conv_channel, kernel_size=3, padding=1, bias=True),
@@ -112,11 +113,15 @@ class CenterHead(nn.Module):
 
     @torch.no_grad()
     def decode(self, preds_dicts, post_cfg):
-        """Heatmap peaks -> boxes (x,y,z,l,w,h,[vx,vy],yaw) with scores/labels above the score threshold,
-        top ``nms_pre_max_size`` per scene (CP/center_head.py:173-328).  The reference then applies rotated
-        NMS (efg._C.nms_gpu) — SURVEY.md §8f row 3, not part of this round."""
-        results = []
+        """Heatmap -> boxes (x,y,z,l,w,h,[vx,vy],yaw); per task and scene: score threshold + centre range mask, rotated
+        NMS (pre / post max size), then the tasks are concatenated with class offsets (CP/center_head.py:173-376).
+        The NMS is csrc/iou3d.cu behind the reference's `rotate_nms_pcdet` convention (CP/box_torch_ops.py:239-264)."""
+        rotate_nms_pcdet = self.rotate_nms
+        if rotate_nms_pcdet is None:
+            from ...operators.iou3d_nms import rotate_nms_pcdet
+
         pc_range, voxel, osf = post_cfg.pc_range, post_cfg.voxel_size, post_cfg.out_size_factor
+        per_task = []
         for task_id, preds in enumerate(preds_dicts):
             hm = preds["hm"].sigmoid()
             b, c, h, w = hm.shape
@@ -129,14 +134,19 @@ class CenterHead(nn.Module):
                 parts += list(preds["vel"].unbind(1))
             boxes = torch.stack(parts + [rot], dim=-1).reshape(b, h * w, -1)
             scores, labels = hm.permute(0, 2, 3, 1).reshape(b, h * w, c).max(dim=-1)
-            results.append((boxes, scores, labels + sum(self.num_classes[:task_id])))
+            limit = boxes.new_tensor(post_cfg.post_center_limit_range)
+            scenes = []
+            for bi in range(b):
+                bx, sc, lb = boxes[bi], scores[bi], labels[bi]
+                mask = (sc > post_cfg.score_threshold) & (bx[:, :3] >= limit[:3]).all(1) & (bx[:, :3] <= limit[3:]).all(1)
+                bx, sc, lb = bx[mask], sc[mask], lb[mask]
+                sel = rotate_nms_pcdet(bx[:, [0, 1, 2, 3, 4, 5, -1]].float(), sc.float(), thresh=post_cfg.nms.nms_iou_threshold,
+                                       pre_maxsize=post_cfg.nms.nms_pre_max_size, post_max_size=post_cfg.nms.nms_post_max_size)
+                scenes.append((bx[sel], sc[sel], lb[sel] + sum(self.num_classes[:task_id])))
+            per_task.append(scenes)
         out = []
-        for bi in range(results[0][0].shape[0]):
-            boxes = torch.cat([r[0][bi] for r in results])
-            scores = torch.cat([r[1][bi] for r in results])
-            labels = torch.cat([r[2][bi] for r in results])
-            k = min(int(post_cfg.nms.nms_pre_max_size), scores.numel())
-            top, idx = scores.topk(k)
-            keep = top > post_cfg.score_threshold
-            out.append({"boxes3d": boxes[idx][keep].cpu(), "scores": top[keep].cpu(), "labels": (labels[idx][keep] + 1).cpu()})
+        for bi in range(len(per_task[0])):
+            out.append({"boxes3d": torch.cat([t[bi][0] for t in per_task]).cpu(),
+                        "scores": torch.cat([t[bi][1] for t in per_task]).cpu(),
+                        "labels": (torch.cat([t[bi][2] for t in per_task]) + 1).cpu()})
         return out

@@ -25,6 +25,7 @@ class VoxelNet(nn.Module):
         self.backbone = SpMiddleResNetFHD(**config.model.backbone, backend=self.backend[0])
         self.neck = RPN(config.model.neck)
         self.center_head = CenterHead(config)
+        self.center_head.rotate_nms = getattr(self.backend[0], "rotate_nms", None)
         a = config.model.loss
         self.out_size_factor = a.out_size_factor
         self.tasks = config.model.head.tasks

@@ -845,12 +845,53 @@ class BoxProjGridSoftmaxFunction(torch.autograd.Function):
 
 
 # --------------------------------------------------------------------------------------------
+# BEV IoU of rotated boxes / rotated NMS (CenterPoint evaluation path)
+# --------------------------------------------------------------------------------------------
+def boxes_bev(boxes_a, boxes_b, overlap=False):
+    """[N,7] x [M,7] (x, y, z, dx, dy, dz, heading) -> [N,M] BEV IoU (or overlap area) of rotated boxes."""
+    _check(boxes_a, "boxes_a", torch.float32)
+    _check(boxes_b, "boxes_b", torch.float32)
+    if boxes_a.dim() != 2 or boxes_b.dim() != 2 or boxes_a.shape[1] != 7 or boxes_b.shape[1] != 7:
+        raise RuntimeError("boxes must be [N, 7]")
+    na, nb = boxes_a.shape[0], boxes_b.shape[0]
+    out = torch.zeros((na, nb), dtype=torch.float32, device=boxes_a.device)
+    L = _lib.lib()
+    ws = workspace(L.efgb_boxes_bev_workspace_bytes(na, nb), boxes_a.device)
+    t0 = PROFILER.begin() if PROFILER is not None else None
+    _lib.check(L.efgb_boxes_bev(_p(boxes_a), na, _p(boxes_b), nb, 1 if overlap else 0, _p(out), _p(ws), ws.numel(), _stream()),
+               "boxes_bev")
+    if t0 is not None:
+        PROFILER.end("boxes_bev", t0, 4 * (7 * (na + nb) + na * nb))
+    return out
+
+
+def nms_bev(boxes_sorted, thresh, normal=False):
+    """Greedy NMS over boxes sorted by descending score.  Returns (keep int64 [N] (first `count` valid), count int32 [1]),
+    both on the device: no host synchronisation."""
+    _check(boxes_sorted, "boxes", torch.float32)
+    if boxes_sorted.dim() != 2 or boxes_sorted.shape[1] != 7:
+        raise RuntimeError("boxes must be [N, 7]")
+    n = boxes_sorted.shape[0]
+    dev = boxes_sorted.device
+    keep = torch.zeros((max(n, 1),), dtype=torch.int64, device=dev)
+    count = torch.zeros((1,), dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    ws = workspace(L.efgb_nms_bev_workspace_bytes(n), dev)
+    t0 = PROFILER.begin() if PROFILER is not None else None
+    _lib.check(L.efgb_nms_bev(_p(boxes_sorted), n, float(thresh), 1 if normal else 0, _p(keep), _p(count), _p(ws), ws.numel(),
+                              _stream()), "nms_bev")
+    if t0 is not None:
+        PROFILER.end("nms_bev", t0, 28 * n + 8 * n * ((n + 63) // 64))
+    return keep, count
+
+
+# --------------------------------------------------------------------------------------------
 # NVTX ranges (SURVEY.md section 5: tracing): one range per operator call, named efgb::<op>
 # --------------------------------------------------------------------------------------------
 _NVTX_OPS = ("hard_voxelize_batched", "dynamic_voxelize", "dynamic_scatter_forward", "dynamic_scatter_backward",
              "subm_rulebook", "sparse_rulebook", "spconv_forward", "spconv_tc", "spconv_tc_wgrad", "spconv_wgrad",
              "split_bf16", "packed_weights", "colsum", "lsa_batched", "sparse_to_dense", "dense_to_sparse",
-             "box_attn_forward", "box_attn_backward", "dense_linear", "fused_ffn", "add_layer_norm")
+             "box_attn_forward", "box_attn_backward", "dense_linear", "fused_ffn", "add_layer_norm", "boxes_bev", "nms_bev")
 _nvtx_on = False
 
 

@@ -213,6 +213,24 @@ int efgb_dense_to_sparse(const float* dense, const int32_t* coords, int64_t num_
                          int batch, const int32_t* grid_dhw_host3, float* feats, efgb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * BEV IoU of rotated boxes and rotated NMS — the CenterPoint evaluation path.
+ * Replaces efg._C.boxes_iou_bev_gpu / boxes_overlap_bev_gpu / nms_gpu / nms_normal_gpu
+ * (efg/operators/src/vision.cpp:100-104, iou3d_nms/iou3d_nms.cpp:22-178, iou3d_nms_kernel.cu:98-342).
+ * Boxes are [x, y, z, dx, dy, dz, heading] f32 rows.  Same polygon-clipping algorithm as the reference (1 cm corner
+ * margin, strict crossings, atan2 ordering), so IoU values agree to fp32 rounding and NMS keeps the same boxes.
+ *   efgb_boxes_bev: out[i * num_b + j] = IoU (mode 0) or overlap area (mode 1) of boxes_a[i] and boxes_b[j].
+ *   efgb_nms_bev:   boxes sorted by descending score; keep[0 .. *num_keep) = indices kept by greedy suppression with
+ *                   IoU > thresh (normal != 0: axis-aligned IoU, heading ignored).  keep (int64 [n]) and num_keep stay on
+ *                   the DEVICE; the reference copies an N x N/64 mask to the host and scans there.
+ * ------------------------------------------------------------------------------------------ */
+size_t efgb_boxes_bev_workspace_bytes(int64_t num_a, int64_t num_b);
+int efgb_boxes_bev(const float* boxes_a, int64_t num_a, const float* boxes_b, int64_t num_b, int mode, float* out,
+                   void* workspace, size_t workspace_bytes, efgb_stream_t stream);
+size_t efgb_nms_bev_workspace_bytes(int64_t n);
+int efgb_nms_bev(const float* boxes_sorted, int64_t n, float thresh, int normal, int64_t* keep, int32_t* num_keep,
+                 void* workspace, size_t workspace_bytes, efgb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Linear sum assignment for a batch of small dense cost matrices that live on the device — the Hungarian
  * matching of HungarianMatcher3d (VD/modules/matcher.py:54-91), which the reference solves on the host
  * with scipy.optimize.linear_sum_assignment after a blocking copy.  Same algorithm and tie-breaking as

@@ -13,6 +13,26 @@ class CpuOracleBackend:
     def box_attn(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, im2col_step):
         return _box.forward(value, spatial_shapes, sampling_locations, attention_weights)
 
+    @staticmethod
+    def rotate_nms(boxes, scores, thresh, pre_maxsize=None, post_max_size=None):
+        """CP/box_torch_ops.py:239-264 over the CPU restatement of the rotated NMS (oracle/iou3d.c)."""
+        import math
+
+        import torch
+
+        from . import iou3d
+
+        b = boxes[:, [0, 1, 2, 4, 3, 5, -1]].clone()
+        b[:, -1] = -b[:, -1] - math.pi / 2
+        order = scores.sort(0, descending=True)[1]
+        if pre_maxsize is not None:
+            order = order[:pre_maxsize]
+        if b.shape[0] == 0:
+            return order[:0]
+        keep = torch.from_numpy(iou3d.nms(b[order].detach().cpu().numpy(), thresh)).to(order.device)
+        sel = order[keep]
+        return sel[:post_max_size] if post_max_size is not None else sel
+
     def __deepcopy__(self, memo):
         return self
 

@@ -81,7 +81,42 @@ def load_box_attn():
     return mod
 
 
+# ---- the reference's CPU BEV IoU (iou3d_cpu.cpp): pins oracle/iou3d.c ---------------------------------------------
+IOU_SRC = "/root/reference/efg/operators/src/iou3d_nms/iou3d_cpu.cpp"
+IOU_NAME = "efg_ref_iou3d"
+
+
+def build_iou3d():
+    if not os.path.exists(IOU_SRC):
+        return None
+    existing = glob.glob(os.path.join(OUT, IOU_NAME + "*.so"))
+    if existing:
+        return existing[0]
+    os.makedirs(OUT, exist_ok=True)
+    from torch.utils.cpp_extension import load
+
+    # the file includes <cuda.h> / <cuda_runtime_api.h> and marks its Point methods __device__ (ignored by g++)
+    load(name=IOU_NAME, sources=[os.path.join(HERE, "ref_iou3d_shim.cpp"), IOU_SRC],
+         extra_cflags=["-O2", "-std=c++17", "-ffp-contract=off"],
+         extra_include_paths=["/root/reference/efg/operators/src", "/usr/local/cuda/include"], build_directory=OUT, verbose=False)
+    existing = glob.glob(os.path.join(OUT, IOU_NAME + "*.so"))
+    return existing[0] if existing else None
+
+
+def load_iou3d():
+    existing = glob.glob(os.path.join(OUT, IOU_NAME + "*.so"))
+    if not existing:
+        return None
+    import torch  # noqa: F401
+
+    spec = importlib.util.spec_from_file_location(IOU_NAME, existing[0])
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 if __name__ == "__main__":
     print(build())
+    print(build_iou3d())
     if "--box-attn" in sys.argv:
         print(build_box_attn())
