@@ -22,6 +22,16 @@ def _replace(x, feats):
     return x.replace_feature(feats)
 
 
+def _fusable_tail(seq, activation):
+    """The sequence is this repo's CUDA SparseSequential (it understands residual= / final_relu=), ends with a
+    BatchNorm1d and the block's activation is a plain ReLU."""
+    import inspect
+
+    mods = list(seq._modules.values()) if hasattr(seq, "_modules") else []
+    return (bool(mods) and isinstance(mods[-1], nn.BatchNorm1d) and isinstance(activation, nn.ReLU) and
+            "residual" in inspect.signature(seq.forward).parameters)
+
+
 class SparseBasicStem(nn.Module):
     """SparseConv3d s2 -> SubM -> SubM, each followed by norm + activation (sparse_net.py:79-95)."""
 
@@ -77,8 +87,11 @@ class SparseBasicResBlock(nn.Module):
         )
 
     def forward(self, x):
-        out = self.conv(x)
         shortcut = self.shortcut(x) if self.shortcut is not None else x
+        if _fusable_tail(self.conv, self.activation):
+            # relu(bn2(conv2(.)) + shortcut): the add and the activation ride in the last norm's fused pass
+            return self.conv(x, residual=shortcut, final_relu=True)
+        out = self.conv(x)
         out = _replace(out, out.features + shortcut.features)
         return _replace(out, self.activation(out.features))
 
@@ -223,8 +236,20 @@ class SparseBasicBlock(nn.Module):
     def forward(self, x):
         identity = x
         out = self.conv1(x)
-        out = _replace(out, self.relu(self.bn1(out.features)))
+        if out.features.is_cuda and isinstance(self.bn1, nn.BatchNorm1d):
+            from .. import ops
+
+            if ops.bn_act_supported(out.features, self.bn1):
+                out = _replace(out, ops.bn_act(out.features, self.bn1, relu=True))
+            else:
+                out = _replace(out, self.relu(self.bn1(out.features)))
+        else:
+            out = _replace(out, self.relu(self.bn1(out.features)))
         out = self.conv2(out)
+        from .. import ops
+
+        if out.features.is_cuda and isinstance(self.bn2, nn.BatchNorm1d) and ops.bn_act_supported(out.features, self.bn2):
+            return _replace(out, ops.bn_act(out.features, self.bn2, residual=identity.features, relu=True))
         out = _replace(out, self.bn2(out.features))
         out = _replace(out, out.features + identity.features)
         return _replace(out, self.relu(out.features))

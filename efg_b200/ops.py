@@ -845,6 +845,70 @@ class BoxProjGridSoftmaxFunction(torch.autograd.Function):
 
 
 # --------------------------------------------------------------------------------------------
+# fused BatchNorm1d (+ residual) (+ ReLU) on the rows of a sparse tensor
+# --------------------------------------------------------------------------------------------
+class _BnActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, training, momentum, eps, relu, want_planes):
+        rows, cols = x.shape
+        L = _lib.lib()
+        y = torch.empty_like(x)
+        mean = torch.empty(cols, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(cols, dtype=torch.float32, device=x.device)
+        planes = torch.empty_like(x) if want_planes else None
+        ws = workspace(L.efgb_bn_workspace_bytes(rows, cols), x.device)
+        t0 = PROFILER.begin() if PROFILER is not None else None
+        rc = L.efgb_bn_forward(_p(x), rows, cols, _p(gamma), _p(beta), _p(residual), 1 if relu else 0, float(eps), float(momentum),
+                               _p(running_mean), _p(running_var), 1 if training else 0, _p(y), _p(mean), _p(rstd), _p(planes),
+                               _p(ws), ws.numel(), _stream())
+        _lib.check(rc, "bn_forward")
+        if t0 is not None:
+            PROFILER.end("bn_act_fwd", t0, 4 * x.numel() * (3 + (1 if residual is not None else 0) + (1 if want_planes else 0)))
+        ctx.save_for_backward(x, y if relu else None, gamma, mean, rstd)
+        ctx.relu, ctx.has_res = bool(relu), residual is not None
+        ctx.mark_non_differentiable(*([planes] if planes is not None else []))
+        return (y, planes) if want_planes else y
+
+    @staticmethod
+    def backward(ctx, dy, *unused):
+        x, y, gamma, mean, rstd = ctx.saved_tensors
+        rows, cols = x.shape
+        dy = dy.contiguous()
+        L = _lib.lib()
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if ctx.has_res else None
+        dgamma = torch.empty(cols, dtype=torch.float32, device=x.device)
+        dbeta = torch.empty(cols, dtype=torch.float32, device=x.device)
+        ws = workspace(L.efgb_bn_workspace_bytes(rows, cols), x.device)
+        t0 = PROFILER.begin() if PROFILER is not None else None
+        rc = L.efgb_bn_backward(_p(dy), _p(x), _p(y), _p(gamma), _p(mean), _p(rstd), rows, cols, 1 if ctx.relu else 0, _p(dx),
+                                _p(dres), _p(dgamma), _p(dbeta), _p(ws), ws.numel(), _stream())
+        _lib.check(rc, "bn_backward")
+        if t0 is not None:
+            PROFILER.end("bn_act_bwd", t0, 4 * x.numel() * (5 + (2 if ctx.relu else 0) + (1 if ctx.has_res else 0)))
+        return dx, dgamma, dbeta, dres, None, None, None, None, None, None, None
+
+
+def bn_act_supported(x, bn):
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous() and bn.affine and
+            (bn.track_running_stats or bn.training) and bn.momentum is not None and
+            bool(_lib.lib().efgb_bn_supported(x.shape[1])))
+
+
+def bn_act(x, bn, residual=None, relu=False, want_planes=False):
+    """y = ReLU(bn(x) [+ residual]) for an nn.BatchNorm1d `bn` on [M, C] rows, one fused pass each way
+    (csrc/batchnorm.cu).  Updates bn.running_mean / running_var / num_batches_tracked like the module would.
+    want_planes: also return the bf16 operand planes of y for the next tensor-core convolution."""
+    training = bn.training or not bn.track_running_stats
+    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    if residual is not None:
+        residual = residual.contiguous()
+    return _BnActFn.apply(x, bn.weight, bn.bias, residual, bn.running_mean if bn.track_running_stats else None,
+                          bn.running_var if bn.track_running_stats else None, training, bn.momentum, bn.eps, relu, want_planes)
+
+
+# --------------------------------------------------------------------------------------------
 # BEV IoU of rotated boxes / rotated NMS (CenterPoint evaluation path)
 # --------------------------------------------------------------------------------------------
 def boxes_bev(boxes_a, boxes_b, overlap=False):
@@ -891,7 +955,7 @@ def nms_bev(boxes_sorted, thresh, normal=False):
 _NVTX_OPS = ("hard_voxelize_batched", "dynamic_voxelize", "dynamic_scatter_forward", "dynamic_scatter_backward",
              "subm_rulebook", "sparse_rulebook", "spconv_forward", "spconv_tc", "spconv_tc_wgrad", "spconv_wgrad",
              "split_bf16", "packed_weights", "colsum", "lsa_batched", "sparse_to_dense", "dense_to_sparse",
-             "box_attn_forward", "box_attn_backward", "dense_linear", "fused_ffn", "add_layer_norm", "boxes_bev", "nms_bev")
+             "box_attn_forward", "box_attn_backward", "dense_linear", "fused_ffn", "add_layer_norm", "boxes_bev", "nms_bev", "bn_act")
 _nvtx_on = False
 
 

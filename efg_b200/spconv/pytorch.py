@@ -58,6 +58,7 @@ class SparseConvTensor:
         self.voxel_num = voxel_num
         self.benchmark = benchmark
         self._rows_sorted = False
+        self._planes = None  # bf16 operand planes of `features` (ops.split_bf16 layout) when a producer emitted them
 
     def replace_feature(self, feature):
         out = SparseConvTensor(feature, self.indices, self.spatial_shape, self.batch_size, self.grid, self.voxel_num,
@@ -100,12 +101,13 @@ class _SparseConvFn(Function):
     rulebook) + wgrad.  ``weight`` is the parameter viewed as [Cout, taps, Cin]."""
 
     @staticmethod
-    def forward(ctx, features, weight, bias, rulebook):
+    def forward(ctx, features, weight, bias, rulebook, planes=None):
         features = features.contiguous()
         weight = weight.contiguous()
         c_out, taps, c_in = weight.shape
         if ops.spconv_tc_supported(c_in, c_out, taps):
-            out = ops.spconv_tc(features, weight, bias, rulebook.nbr, 0)
+            # `planes`: bf16 operand planes of `features` already produced by the fused BN + ReLU pass upstream
+            out = ops.spconv_tc(features, weight, bias, rulebook.nbr, 0, planes=planes)
         else:
             out = ops.spconv_forward(features, weight.permute(1, 2, 0).contiguous(), bias, rulebook.nbr)
         ctx.rulebook = rulebook
@@ -138,7 +140,7 @@ class _SparseConvFn(Function):
                 d_w = ops.spconv_wgrad(features, grad_out, rb.nbr, taps, c_in, c_out).permute(2, 0, 1).contiguous()
         if ctx.has_bias and ctx.needs_input_grad[2]:
             d_b = grad_out.sum(0)
-        return d_feat, d_w, d_b, None
+        return d_feat, d_w, d_b, None, None
 
 
 def strided_rulebook(x, kernel_size, stride, padding):
@@ -162,6 +164,15 @@ class SparseModule(nn.Module):
 
 def _is_sparse_module(m):
     return isinstance(m, SparseModule)
+
+
+def _wants_planes(module, channels):
+    """True when `module` is a sparse conv that will take the pre-split tensor-core path on `channels` inputs."""
+    if not isinstance(module, SparseConvolution) or ops.CONV_PRECISION != "bf16x3" or not ops.USE_PLANES:
+        return False
+    taps = int(module.kernel_size[0] * module.kernel_size[1] * module.kernel_size[2])
+    return taps > 1 and module.in_channels == channels and ops.spconv_tc_supported(channels, module.out_channels, taps) and \
+        bool(ops._lib.lib().efgb_spconv_tc_planes_supported(channels, module.out_channels, taps))
 
 
 class SparseSequential(SparseModule):
@@ -200,15 +211,42 @@ class SparseSequential(SparseModule):
                 raise KeyError("name exists")
         self.add_module(name, module)
 
-    def forward(self, input):
-        for module in self._modules.values():
+    def forward(self, input, residual=None, final_relu=False):
+        """`residual` / `final_relu`: fold `relu(x + residual)` of a residual block into the LAST BatchNorm1d of the
+        sequence (only valid when the sequence ends with that norm; the blocks of sparse_backbone.py use it)."""
+        mods = list(self._modules.values())
+        i = 0
+        while i < len(mods):
+            module = mods[i]
             if _is_sparse_module(module):
                 input = module(input)
             elif isinstance(input, SparseConvTensor):
                 if input.indices.shape[0] != 0:
-                    input = input.replace_feature(module(input.features))
+                    if isinstance(module, nn.BatchNorm1d) and ops.bn_act_supported(input.features, module):
+                        # BatchNorm1d [+ residual] [+ ReLU] in one fused pass each way (csrc/batchnorm.cu), emitting the
+                        # operand planes of the result when a tensor-core conv consumes it next
+                        span = 2 if (i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)) else 1
+                        tail = i + span == len(mods)
+                        relu = span == 2 or (tail and final_relu)
+                        res = residual.features if (tail and residual is not None) else None
+                        consumer = mods[i + span] if i + span < len(mods) else None
+                        want = _wants_planes(consumer, input.features.shape[1])
+                        out = ops.bn_act(input.features, module, residual=res, relu=relu, want_planes=want)
+                        feats, planes = out if want else (out, None)
+                        input = input.replace_feature(feats)
+                        input._planes = planes
+                        if tail:
+                            residual, final_relu = None, False
+                        i += span - 1
+                    else:
+                        input = input.replace_feature(module(input.features))
             else:
                 input = module(input)
+            i += 1
+        if residual is not None:   # the sequence did not end with a fusable norm: plain add + activation
+            input = input.replace_feature(input.features + residual.features)
+        if final_relu:
+            input = input.replace_feature(torch.relu(input.features))
         return input
 
 
@@ -273,7 +311,8 @@ class SparseConvolution(SparseModule):
         assert isinstance(x, SparseConvTensor), "sparse convolution expects a SparseConvTensor"
         rb = self._rulebook(x)
         taps = self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2]
-        feats = _SparseConvFn.apply(x.features, self.weight.view(self.out_channels, taps, self.in_channels), self.bias, rb)
+        feats = _SparseConvFn.apply(x.features, self.weight.view(self.out_channels, taps, self.in_channels), self.bias, rb,
+                                    getattr(x, "_planes", None))
         out = SparseConvTensor(feats, rb.out_indices, rb.out_shape, x.batch_size, x.grid, x.voxel_num, x.indice_dict,
                                x.benchmark)
         out._rows_sorted = x._rows_sorted if self.subm else True

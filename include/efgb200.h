@@ -213,6 +213,26 @@ int efgb_dense_to_sparse(const float* dense, const int32_t* coords, int64_t num_
                          int batch, const int32_t* grid_dhw_host3, float* feats, efgb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * BatchNorm1d over the active rows of a sparse tensor fused with the residual add and ReLU that follow it in the
+ * reference's blocks: y = ReLU(BN(x) [+ residual])  (efg/modeling/backbones/sparse_net.py:85-95,135-147,162-163,455-469;
+ * nn.BatchNorm1d semantics: batch statistics over the rows, biased variance for normalisation, unbiased for the running
+ * estimate, momentum update in place).  training == 0 uses the running statistics.  `planes` (nullable) receives the
+ * bf16 hi / lo operand planes of y for the next tensor-core convolution (see efgb_split_bf16).
+ * Backward: dx, dgamma, dbeta and (dres nullable) the gradient of the residual; y is read for the ReLU mask.
+ * Supported when cols % 4 == 0 and 256 % (cols / 4) == 0.
+ * ------------------------------------------------------------------------------------------ */
+int efgb_bn_supported(int cols);
+size_t efgb_bn_workspace_bytes(int64_t rows, int cols);
+int efgb_bn_forward(const float* x, int64_t rows, int cols, const float* gamma, const float* beta,
+                    const float* residual /* nullable */, int relu, float eps, float momentum,
+                    float* running_mean /* nullable in training */, float* running_var, int training, float* y,
+                    float* save_mean, float* save_rstd, void* planes /* nullable */, void* workspace,
+                    size_t workspace_bytes, efgb_stream_t stream);
+int efgb_bn_backward(const float* dy, const float* x, const float* y, const float* gamma, const float* save_mean,
+                     const float* save_rstd, int64_t rows, int cols, int relu, float* dx, float* dres /* nullable */,
+                     float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, efgb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * BEV IoU of rotated boxes and rotated NMS — the CenterPoint evaluation path.
  * Replaces efg._C.boxes_iou_bev_gpu / boxes_overlap_bev_gpu / nms_gpu / nms_normal_gpu
  * (efg/operators/src/vision.cpp:100-104, iou3d_nms/iou3d_nms.cpp:22-178, iou3d_nms_kernel.cu:98-342).
