@@ -311,3 +311,42 @@ extern "C" int efgb_nms_bev(const float* boxes_sorted, int64_t n, float thresh, 
   EFGB_LAUNCH_OK("iou3d::nms_scan_kernel");
   return EFGB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// CenterPoint label assignment, the heatmap part (CP/voxelnet.py:44-192 -> CP/center_utils.py:29-58 draw_gaussian):
+// one CTA per object splats its Gaussian (sigma = (2 r + 1) / 6, clipped to the map) into heatmap[scene, class] with
+// max() — order independent, so all objects of the batch are drawn concurrently with an integer atomicMax on the
+// (non-negative) float bits.  The reference draws them one after another in numpy on the host and uploads the maps.
+// ------------------------------------------------------------------------------------------------------------------
+namespace efgb {
+__global__ void __launch_bounds__(128)
+draw_gaussians_kernel(const int32_t* __restrict__ obj, int num_obj, int height, int width, float* __restrict__ heatmaps) {
+  // obj[i] = (plane index, x, y, radius): plane = flattened (scene, class) map
+  const int i = blockIdx.x;
+  if (i >= num_obj) return;
+  const int plane = obj[4 * i], cx = obj[4 * i + 1], cy = obj[4 * i + 2], r = obj[4 * i + 3];
+  const int d = 2 * r + 1;
+  const double sigma = static_cast<double>(d) / 6.0;
+  const double inv = 1.0 / (2.0 * sigma * sigma);
+  float* hm = heatmaps + static_cast<int64_t>(plane) * height * width;
+  for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
+    const int dy = e / d - r, dx = e % d - r;
+    const int y = cy + dy, x = cx + dx;
+    if (x < 0 || x >= width || y < 0 || y >= height) continue;
+    // numpy evaluates the Gaussian in float64 and stores into the float32 map
+    const float v = static_cast<float>(exp(-static_cast<double>(dx * dx + dy * dy) * inv));
+    atomicMax(reinterpret_cast<int*>(hm + static_cast<int64_t>(y) * width + x), __float_as_int(v));
+  }
+}
+}  // namespace efgb
+
+extern "C" int efgb_draw_gaussians(const int32_t* objects, int num_objects, int height, int width, float* heatmaps,
+                                   efgb_stream_t stream_) {
+  cudaStream_t stream = as_stream(stream_);
+  EFGB_REQUIRE(num_objects >= 0 && height > 0 && width > 0, EFGB_EINVAL, "draw_gaussians: bad argument");
+  if (num_objects == 0) return EFGB_OK;
+  EFGB_REQUIRE(objects && heatmaps, EFGB_EINVAL, "draw_gaussians: null pointer");
+  draw_gaussians_kernel<<<num_objects, 128, 0, stream>>>(objects, num_objects, height, width, heatmaps);
+  EFGB_LAUNCH_OK("draw_gaussians_kernel");
+  return EFGB_OK;
+}

@@ -53,6 +53,11 @@ class VoxelNet(nn.Module):
 
     def label_assign(self, infos):
         ds = self.config.dataset
+        if self.device.type == "cuda" and getattr(self.backend[0], "name", "") == "efgb200-cuda":
+            from .assign import assign_batch_device
+
+            return assign_batch_device(infos, self.tasks, self.grid_size, ds.pc_range, ds.voxel_size, self.out_size_factor,
+                                       self.gaussian_overlap, self._max_objs, self._min_radius, self.device)
         per_scene = [assign_scene(info["annotations"], self.tasks, self.grid_size, ds.pc_range, ds.voxel_size,
                                   self.out_size_factor, self.gaussian_overlap, self._max_objs, self._min_radius)
                      for info in infos]

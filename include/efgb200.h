@@ -250,6 +250,12 @@ size_t efgb_nms_bev_workspace_bytes(int64_t n);
 int efgb_nms_bev(const float* boxes_sorted, int64_t n, float thresh, int normal, int64_t* keep, int32_t* num_keep,
                  void* workspace, size_t workspace_bytes, efgb_stream_t stream);
 
+/* CenterPoint label assignment, heatmap part (CP/voxelnet.py:44-192, CP/center_utils.py:29-58): objects[i] = (plane, x, y,
+ * radius) int32 on the device; heatmaps [planes, height, width] f32, zero-initialised by the caller; every object's
+ * Gaussian (sigma = (2 r + 1) / 6) is max-ed into its plane.  Replaces the host numpy drawing + upload of the maps. */
+int efgb_draw_gaussians(const int32_t* objects, int num_objects, int height, int width, float* heatmaps,
+                        efgb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Linear sum assignment for a batch of small dense cost matrices that live on the device — the Hungarian
  * matching of HungarianMatcher3d (VD/modules/matcher.py:54-91), which the reference solves on the host
