@@ -250,6 +250,19 @@ size_t efgb_nms_bev_workspace_bytes(int64_t n);
 int efgb_nms_bev(const float* boxes_sorted, int64_t n, float thresh, int normal, int64_t* keep, int32_t* num_keep,
                  void* workspace, size_t workspace_bytes, efgb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Point-cloud augmentation on the device: RandomFlip3D -> GlobalRotation -> GlobalScaling ->
+ * GlobalTranslation -> FilterByRange of efg/data/augmentations/extend_3d.py:121-316 applied to points [n, nfeat] f32
+ * (x, y, z first) with the random draws supplied by the caller; the kept points are written in their original order to
+ * out_points (capacity n rows) and their number to out_count (device int32) — no host synchronisation, the count
+ * can feed efgb_hard_voxelize's scene offsets directly.  range_host6 == NULL: no filtering.
+ * ------------------------------------------------------------------------------------------ */
+size_t efgb_augment_workspace_bytes(int64_t n);
+int efgb_augment_points(const float* points, int64_t n, int nfeat, int flip_x, int flip_y, float cosa, float sina,
+                        float scale, const float* translation_host3 /* nullable */, const float* range_host6 /* nullable */,
+                        float* out_points, int32_t* out_count, void* workspace, size_t workspace_bytes,
+                        efgb_stream_t stream);
+
 /* CenterPoint label assignment, heatmap part (CP/voxelnet.py:44-192, CP/center_utils.py:29-58): objects[i] = (plane, x, y,
  * radius) int32 on the device; heatmaps [planes, height, width] f32, zero-initialised by the caller; every object's
  * Gaussian (sigma = (2 r + 1) / 6) is max-ed into its plane.  Replaces the host numpy drawing + upload of the maps. */
