@@ -71,6 +71,9 @@ VARIANTS = {
     "abl4": ["-DEFGB_TC_ABLATE=4"],
     "abl6": ["-DEFGB_TC_ABLATE=6"],
     "abl7": ["-DEFGB_TC_ABLATE=7"],
+    "abl8": ["-DEFGB_TC_ABLATE=8"],
+    "sb2": ["-DEFGB_TC_SB_MID=2"],
+    "trace": ["-DEFGB_TC_TRACE=1"],    # pipeline time stamps of CTA 0 (scripts/trace_conv.py)
 }
 
 

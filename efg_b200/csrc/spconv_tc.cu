@@ -37,6 +37,14 @@
 namespace efgb {
 namespace tc {
 
+#if EFGB_TC_TRACE
+constexpr int kTraceStages = 2048;
+__device__ long long g_trace[kTraceStages * 12];
+#define EFGB_TRACE(stage, slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (stage) < kTraceStages) g_trace[(stage) * 12 + (slot)] = clock64(); } while (0)
+#else
+#define EFGB_TRACE(stage, slot) do { } while (0)
+#endif
+
 constexpr int kTileM = 128;
 constexpr int kChunkK = 32;             // tf32 values per K chunk (128 bytes)
 constexpr int kBf16ChunkK = 64;         // bf16 values per K chunk (128 bytes)
@@ -44,6 +52,7 @@ constexpr int kBf16ChunkK = 64;         // bf16 values per K chunk (128 bytes)
 #define EFGB_TC_PRODUCER_WARPS 16
 #endif
 constexpr int kProducerWarps = EFGB_TC_PRODUCER_WARPS;   // gather / split warps (8 or 16)
+constexpr int kEpiStageBytes = 32 * 16 * 4;                // per epilogue warp: a 32-row x 16-column fp32 block
 constexpr int kMmaWarp = kProducerWarps;
 constexpr int kLoaderWarp = kProducerWarps + 1;
 constexpr int kThreads = (kProducerWarps + 6) * 32;      // + MMA issuer, weight loader, 4 epilogue warps
@@ -54,6 +63,18 @@ constexpr int kMaxTaps = 32;
 enum : int { kTf32 = 0, kTf32x3 = 1, kBf16x3 = 2 };
 // Perf ablations for A/B library variants only (efg_b200/_build.py VARIANTS; results are invalid): 1 = MMAs skipped,
 // 2 = planes producers skip the copies, 4 = planes producers skip the rulebook loads.  The product build defines nothing.
+// EFGB_TC_TRACE=1 (diagnostic build only): CTA 0 writes clock64() stamps of every pipeline stage into g_trace —
+// producer warp 0: [0] before the a_empty wait, [1] after it, [2] copies issued, [3] stage n - depth completed;
+// MMA warp: [4] a_full acquired, [5] MMAs + commit issued.  Read back with efgb_debug_trace_read.
+#ifndef EFGB_TC_TRACE
+#define EFGB_TC_TRACE 0
+#endif
+#ifndef EFGB_TC_SB_MID
+#define EFGB_TC_SB_MID 3    // weight-ring depth for 16..63 KB chunks
+#endif
+#ifndef EFGB_TC_MAX_T
+#define EFGB_TC_MAX_T 8     // row tiles per super-tile (accumulators side by side in TMEM)
+#endif
 #ifndef EFGB_TC_ABLATE
 #define EFGB_TC_ABLATE 0
 #endif
@@ -207,6 +228,8 @@ struct Params {
   int concat;            // 1: A_hi x [B_hi | B_lo] as one MMA of N = 2 n_cta (+ A_lo x B_hi); 0: three MMAs of N = n_cta
   int tiles_per_super;   // T: row tiles that share every weight chunk (accumulators side by side in TMEM)
   int num_super;         // ceil(num_tiles / T)
+  int wide;              // bf16x3 register path: 8-value units (input 32-byte aligned)
+  int epi_staged;        // epilogue through the shared-memory staging buffers (coalesced stores); 0: row-per-thread stores
   int sa, sb;            // A-ring / B-ring depth
   int cred_shift;        // log2(c_red) when c_red is a power of two, else -1
 };
@@ -339,8 +362,11 @@ __device__ __forceinline__ void produce_a(const Params& p, const CtaWork& w, uin
   };
   int slot = 0;
   uint32_t phase = 0;
+  [[maybe_unused]] int t_fin = 0;
   auto finish = [&](const float4 (&v)[kJ][2]) {
+    if (tid == 0) EFGB_TRACE(t_fin, 0);
     mbar_wait(smem_u32(&a_empty[slot]), phase ^ 1);
+    if (tid == 0) EFGB_TRACE(t_fin, 1);
     uint8_t* a_hi = a_ring + static_cast<size_t>(slot) * a_bytes;
     uint8_t* a_lo = a_hi + a_part;
 #pragma unroll
@@ -348,6 +374,7 @@ __device__ __forceinline__ void produce_a(const Params& p, const CtaWork& w, uin
       convert_store<kMode>(a_hi, a_lo, off[j], v[j][0]);
       convert_store<kMode>(a_hi, a_lo, off[j] + 64u * 128u, v[j][1]);
     }
+    if (tid == 0) EFGB_TRACE(t_fin, 2);
     // No fence.proxy.async here: it lowers to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, and the MEMBAR waits for EVERY
     // outstanding memory operation of the thread — including the gathers of the next stage, which serialised the
     // software pipeline on one full memory latency per stage (measured: ~1600 cycles per stage whatever the producer
@@ -358,6 +385,12 @@ __device__ __forceinline__ void produce_a(const Params& p, const CtaWork& w, uin
 #endif
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&a_full[slot]));
+    if (tid == 0) {
+      EFGB_TRACE(t_fin, 3);
+      EFGB_TRACE(t_fin, 9);
+      EFGB_TRACE(t_fin, 10);
+    }
+    ++t_fin;
     if (++slot == p.sa) {
       slot = 0;
       phase ^= 1;
@@ -378,6 +411,131 @@ __device__ __forceinline__ void produce_a(const Params& p, const CtaWork& w, uin
     if (s + 1 < total) {
       if (s + 2 < total) gather(src_a, ci_a, v_a);
       if (s + 3 < total) load_idx(src_b, ci_b);
+      finish(v_b);
+    }
+  }
+}
+
+// bf16x3 register path with 8-value units (dense GEMMs and the channel counts the cp.async path does not take): one
+// LDG.256 per unit and one 16-byte shared-memory store per operand image, i.e. half the load / store instructions of the
+// 4-value path above.  The pipeline traces (scripts/trace_conv.py) showed that path bound by the load/store unit's queue:
+// every LDG / STS of the producers AND of the epilogue warps waited in it (a 4-store epilogue block took ~300 cycles).
+// Needs a 32-byte aligned input and c_red % 8 == 0.  Eight lanes own a tile row (lane l: 16-byte piece l of the 128-byte
+// hi / lo rows), a warp stores four full rows per instruction: conflict-free under the 128-byte swizzle.
+struct Wide8 {
+  float4 a, b;
+};
+__device__ __forceinline__ Wide8 ldg256(const float* ptr) {
+  Wide8 v;
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v.a.x), "=f"(v.a.y), "=f"(v.a.z), "=f"(v.a.w), "=f"(v.b.x), "=f"(v.b.y), "=f"(v.b.z), "=f"(v.b.w)
+               : "l"(ptr));
+  return v;
+}
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(x - __uint_as_float(hi << 16), y - __uint_as_float(hi & 0xFFFF0000u));
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void produce_a_wide(const Params& p, const CtaWork& w, uint8_t* a_ring, uint64_t* a_full,
+                                               uint64_t* a_empty, const int tid, const int lane) {
+  static_assert(kProducerWarps == 16, "the row-slot mapping assumes 64 row slots of 8 lanes");
+  constexpr int a_part = kTileM * 128;
+  constexpr int a_bytes = 2 * a_part;
+  const int total = w.total_a;
+  if (total == 0) return;
+  const int l = tid & 7;
+  const int r_lo = tid >> 3;   // rows r_lo and r_lo + 64
+  const uint32_t off = static_cast<uint32_t>(r_lo) * 128u + (static_cast<uint32_t>(l ^ (r_lo & 7)) << 4);
+  const uint32_t c_red = static_cast<uint32_t>(p.c_red);
+  struct Src {
+    int32_t e[2];     // source rows of tile rows r_lo, r_lo + 64 (-1: nothing)
+    uint32_t ci;      // first channel of the unit inside its tap
+  };
+  int cu_s = 0, cu_c = 0, cu_t = 0, cu_ti = w.tiles_in(p, 0);
+  auto load_idx = [&](Src& x) {
+    const int tile = (static_cast<int>(blockIdx.x) + cu_s * static_cast<int>(gridDim.x)) * p.tiles_per_super + cu_t;
+    const int row0 = tile * kTileM + r_lo;
+    const bool ok0 = row0 < p.num_out, ok1 = row0 + 64 < p.num_out;
+    const int kk = cu_c * kBf16ChunkK + 8 * l;
+    const int tap = p.cred_shift >= 0 ? (kk >> p.cred_shift) : kk / p.c_red;
+    x.ci = static_cast<uint32_t>(kk - tap * p.c_red);
+    const bool tap_ok = tap < p.taps;
+    if (p.nbr) {
+      const int32_t* n0 = p.nbr + static_cast<int64_t>(row0) * p.taps + tap;
+      x.e[0] = (tap_ok && ok0) ? __ldg(n0) : -1;
+      x.e[1] = (tap_ok && ok1) ? __ldg(n0 + 64 * p.taps) : -1;
+    } else {
+      x.e[0] = (tap_ok && ok0) ? row0 : -1;
+      x.e[1] = (tap_ok && ok1) ? row0 + 64 : -1;
+    }
+    if (++cu_t == cu_ti) {
+      cu_t = 0;
+      if (++cu_c == p.chunks) {
+        cu_c = 0;
+        ++cu_s;
+        cu_ti = w.tiles_in(p, cu_s);
+      }
+    }
+  };
+  auto gather = [&](const Src& x, Wide8 (&v)[2]) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      v[i].a = make_float4(0.f, 0.f, 0.f, 0.f);
+      v[i].b = make_float4(0.f, 0.f, 0.f, 0.f);
+      // 32-bit element offset (the host checks num_in * c_red < 2^32)
+      if (x.e[i] >= 0) v[i] = ldg256(p.in + static_cast<size_t>(static_cast<uint32_t>(x.e[i]) * c_red + x.ci));
+    }
+  };
+  int slot = 0;
+  uint32_t phase = 0;
+  [[maybe_unused]] int t_fin = 0;
+  auto finish = [&](const Wide8 (&v)[2]) {
+    if (tid == 0) EFGB_TRACE(t_fin, 0);
+    mbar_wait(smem_u32(&a_empty[slot]), phase ^ 1);
+    if (tid == 0) EFGB_TRACE(t_fin, 1);
+    uint8_t* a_hi = a_ring + static_cast<size_t>(slot) * a_bytes;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      uint4 hi, lo;
+      split2(v[i].a.x, v[i].a.y, hi.x, lo.x);
+      split2(v[i].a.z, v[i].a.w, hi.y, lo.y);
+      split2(v[i].b.x, v[i].b.y, hi.z, lo.z);
+      split2(v[i].b.z, v[i].b.w, hi.w, lo.w);
+      *reinterpret_cast<uint4*>(a_hi + off + static_cast<uint32_t>(i) * (64u * 128u)) = hi;
+      *reinterpret_cast<uint4*>(a_hi + a_part + off + static_cast<uint32_t>(i) * (64u * 128u)) = lo;
+    }
+    if (tid == 0) EFGB_TRACE(t_fin, 2);
+#if !EFGB_TC_FENCE_AT_MMA
+    fence_proxy_async();
+#endif
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&a_full[slot]));
+    if (tid == 0) {
+      EFGB_TRACE(t_fin, 3);
+      EFGB_TRACE(t_fin, 9);
+      EFGB_TRACE(t_fin, 10);
+    }
+    ++t_fin;
+    if (++slot == p.sa) {
+      slot = 0;
+      phase ^= 1;
+    }
+  };
+  Src src_a, src_b;
+  Wide8 v_a[2], v_b[2];
+  load_idx(src_a);
+  gather(src_a, v_a);
+  if (total > 1) load_idx(src_b);
+  for (int s = 0; s < total; s += 2) {
+    // stage s is in v_a; the rulebook entries of stage s+1 are in src_b
+    if (s + 1 < total) gather(src_b, v_b);
+    if (s + 2 < total) load_idx(src_a);
+    finish(v_a);
+    if (s + 1 < total) {
+      if (s + 2 < total) gather(src_a, v_a);
+      if (s + 3 < total) load_idx(src_b);
       finish(v_b);
     }
   }
@@ -468,6 +626,7 @@ __device__ __forceinline__ void produce_a_planes(const Params& p, const CtaWork&
       x.v[1][0] = (tap_ok && ok0) ? __ldg(p.nbr + (e0 + tap)) : -1;
       x.v[1][1] = (tap_ok && ok1) ? __ldg(p.nbr + (e1 + tap)) : -1;
     }
+    if constexpr ((EFGB_TC_ABLATE & 8) != 0) x.v[0][0] = x.v[0][1] = x.v[1][0] = x.v[1][1] = -1;
     if (++cu_t == cu_ti) {
       cu_t = 0;
       if (++cu_c == p.chunks) {
@@ -479,8 +638,11 @@ __device__ __forceinline__ void produce_a_planes(const Params& p, const CtaWork&
   };
   int islot = 0;
   uint32_t iphase = 0;
+  [[maybe_unused]] int t_issue = 0, t_done = 0;
   auto issue = [&](const Idx& x) {   // copies of the stage whose rulebook entries are in x
+    if (tid == 0) EFGB_TRACE(t_issue, 0);
     mbar_wait(smem_u32(&a_empty[islot]), iphase ^ 1);
+    if (tid == 0) EFGB_TRACE(t_issue, 1);
     const uint32_t dst = a_base + static_cast<uint32_t>(islot) * static_cast<uint32_t>(a_bytes);
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
@@ -492,6 +654,8 @@ __device__ __forceinline__ void produce_a_planes(const Params& p, const CtaWork&
         if constexpr ((EFGB_TC_ABLATE & 2) == 0) cp_async_16(dst + dst_off[k] + static_cast<uint32_t>(i * 64 * 128), g, e < 0 ? 0u : 16u);
       }
     }
+    if (tid == 0) EFGB_TRACE(t_issue, 2);
+    ++t_issue;
     if (++islot == p.sa) {
       islot = 0;
       iphase ^= 1;
@@ -500,12 +664,16 @@ __device__ __forceinline__ void produce_a_planes(const Params& p, const CtaWork&
   int cslot = 0;
   auto complete = [&]() {
     cp_async_commit();                   // possibly empty: one group per stage keeps the wait count constant
+    if (tid == 0) EFGB_TRACE(t_done, 9);
     cp_async_wait<kPlaneDepth>();        // the copies of the oldest stage in flight have landed
+    if (tid == 0) EFGB_TRACE(t_done, 3);
 #if !EFGB_TC_FENCE_AT_MMA
     fence_proxy_async();                 // -> visible to the tensor core (async proxy)
 #endif
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&a_full[cslot]));
+    if (tid == 0) EFGB_TRACE(t_done, 10);
+    ++t_done;
     if (++cslot == p.sa) cslot = 0;
   };
 
@@ -577,9 +745,11 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p) 
   uint64_t* tmem_full = b_empty + p.sb;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(tmem_slot + 4);   // 4 x kEpiStageBytes, 16-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) EFGB_TRACE(0, 6);
 
   // TMEM: two sets of T accumulators of acc_cols fp32 columns each, power of two >= 32
   uint32_t tmem_cols = 32;
@@ -610,12 +780,15 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p) 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const CtaWork w(p);
+  if (threadIdx.x == 0) EFGB_TRACE(1, 6);
 
   if (warp < kProducerWarps) {
     // ================= A producers =================
     if constexpr (kMode == kBf16x3) {
       if (p.planes)
         produce_a_planes(p, w, a_ring, a_full, a_empty, static_cast<int>(threadIdx.x), lane);
+      else if (p.wide)
+        produce_a_wide(p, w, a_ring, a_full, a_empty, static_cast<int>(threadIdx.x), lane);
       else
         produce_a<kMode>(p, w, a_ring, a_full, a_empty, static_cast<int>(threadIdx.x), lane);
     } else {
@@ -630,7 +803,25 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p) 
       const uint32_t part_bytes = static_cast<uint32_t>(b_part);
       int stage = 0;
       uint32_t phase = 0;
+      // Dense GEMM (identity rulebook): the rows of a super-tile are one contiguous block of the input; pull the NEXT
+      // one into L2 a whole super-tile ahead of the producers' loads.  The activations of a token-wise linear come
+      // from HBM (ncu: 55 % L2 hit rate, 46 % of the stall samples on the first use of a loaded value), and the
+      // register pipeline keeps only one stage of loads in flight.
+      auto prefetch_super = [&](int i) {
+        if (p.nbr != nullptr || p.in == nullptr || blockIdx.y != 0 || i >= w.n_super) return;
+        const int64_t st1 = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(i) * gridDim.x;
+        const int64_t r0 = st1 * T * kTileM;
+        const int64_t r1 = r0 + T * kTileM < p.num_out ? r0 + T * kTileM : p.num_out;
+        const int64_t bytes = (r1 - r0) * p.c_red * 4;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.in) + r0 * p.c_red * 4;
+        for (int64_t o = 0; o < bytes; o += 65536) {
+          const uint32_t n = static_cast<uint32_t>(bytes - o < 65536 ? bytes - o : 65536);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + o), "r"(n) : "memory");
+        }
+      };
       for (int i = 0; i < w.n_super; ++i) {
+        if (i == 0) prefetch_super(0);
+        prefetch_super(i + 1);
         for (int c = 0; c < p.chunks; ++c) {
           mbar_wait(smem_u32(&b_empty[stage]), phase ^ 1);
           const uint32_t bar = smem_u32(&b_full[stage]);
@@ -665,6 +856,7 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p) 
       const uint32_t b_full_u = smem_u32(b_full), b_empty_u = smem_u32(b_empty);
       int sa_ = 0, sb_ = 0;
       uint32_t pa = 0, pb = 0;
+      [[maybe_unused]] int t_mma = 0;
       for (int i = 0; i < w.n_super; ++i) {
         const int acc = i & 1;
         const uint32_t acc_phase = static_cast<uint32_t>((i >> 1) & 1);
@@ -678,9 +870,11 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p) 
           const uint64_t db_lo = make_desc_sw128(b_hi + b_part);
           for (int t = 0; t < ti; ++t) {
             mbar_wait(a_full_u + sa_ * 8, pa);
+            if (lane == 0) EFGB_TRACE(t_mma, 4);
 #if EFGB_TC_FENCE_AT_MMA
             fence_proxy_async();   // the producers' generic-proxy writes (acquired above) -> visible to the async proxy
 #endif
+            if (lane == 0 && t_mma >= 10) EFGB_TRACE(t_mma, 6);
             tc_fence_after();
             const uint32_t a_hi = a_ring_u + static_cast<uint32_t>(sa_ * a_bytes);
             const uint64_t da_hi = make_desc_sw128(a_hi);
@@ -704,9 +898,12 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p) 
                   tc_mma<kMode>(tmem_d, da_hi + adv, db_hi + adv, idesc_n, accum);
                 }
               }
+              if (t_mma >= 10) EFGB_TRACE(t_mma, 7);
               tc_commit(a_empty_u + sa_ * 8);  // A stage reusable once these MMAs have read it
             }
             __syncwarp();
+            if (lane == 0) EFGB_TRACE(t_mma, 5);
+            ++t_mma;
             if (++sa_ == p.sa) {
               sa_ = 0;
               pa ^= 1;
@@ -726,16 +923,20 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p) 
   } else {
     // ================= epilogue (4 warps; warp w may only touch TMEM lanes 32*(w%4)..+31) =================
     const int quarter = warp & 3;
+    uint8_t* stage_w = epi_stage + quarter * kEpiStageBytes;
     for (int i = 0; i < w.n_super; ++i) {
       const int acc = i & 1;
       const int ti = w.tiles_in(p, i);
       const int st = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
       mbar_wait(smem_u32(&tmem_full[acc]), static_cast<uint32_t>((i >> 1) & 1));
       tc_fence_after();
+      if (quarter == 0 && lane == 0) EFGB_TRACE(2 + 2 * i, 6);
       for (int t = 0; t < ti; ++t) {
-        const int64_t row = (static_cast<int64_t>(st) * T + t) * kTileM + quarter * 32 + lane;
+        const int64_t row0 = (static_cast<int64_t>(st) * T + t) * kTileM + quarter * 32;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>((acc * T + t) * p.acc_cols);
         for (int c0 = 0; c0 < n_cta; c0 += 16) {
+          [[maybe_unused]] const bool tr = quarter == 0 && lane == 0 && i == 1 && t == 0;
+          if (tr) EFGB_TRACE(1000 + (c0 >> 4), 0);
           uint32_t r[16];
           tc_ld16(taddr + c0, r);
           if (p.concat) {
@@ -747,34 +948,72 @@ __global__ void __launch_bounds__(kThreads, 1) spconv_tc_kernel(const Params p) 
           } else {
             tc_wait_ld();
           }
-          if (row < p.num_out) {
-            float* dst = p.out + row * p.n_out + n0 + c0;
+          if (tr) EFGB_TRACE(1000 + (c0 >> 4), 1);
+          // A thread holds 16 columns of ITS row: stored directly, a warp instruction would touch 32 rows (32 L1TEX
+          // wavefronts per 512 bytes — measured: 16.6 k cycles per 128 x 256 tile, more than the tile's main loop).
+          // The 32 x 16 block goes through a 2 KB staging buffer (XOR-swizzled 16-byte pieces, conflict-free both
+          // ways) and leaves as 8 rows x 64 contiguous bytes per instruction.
+          if (!p.epi_staged) {
+            // no room for the staging buffers (256-column CTAs with two operand images): row-per-thread stores
+            const int64_t row = row0 + lane;
+            if (row < p.num_out) {
+              float* dst = p.out + row * p.n_out + n0 + c0;
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              float4 o;
-              o.x = __uint_as_float(r[j + 0]) + (p.bias ? p.bias[n0 + c0 + j + 0] : 0.f);
-              o.y = __uint_as_float(r[j + 1]) + (p.bias ? p.bias[n0 + c0 + j + 1] : 0.f);
-              o.z = __uint_as_float(r[j + 2]) + (p.bias ? p.bias[n0 + c0 + j + 2] : 0.f);
-              o.w = __uint_as_float(r[j + 3]) + (p.bias ? p.bias[n0 + c0 + j + 3] : 0.f);
-              if (p.relu) {
-                o.x = fmaxf(o.x, 0.f);
-                o.y = fmaxf(o.y, 0.f);
-                o.z = fmaxf(o.z, 0.f);
-                o.w = fmaxf(o.w, 0.f);
+              for (int j = 0; j < 16; j += 4) {
+                float4 o;
+                o.x = __uint_as_float(r[j + 0]) + (p.bias ? p.bias[n0 + c0 + j + 0] : 0.f);
+                o.y = __uint_as_float(r[j + 1]) + (p.bias ? p.bias[n0 + c0 + j + 1] : 0.f);
+                o.z = __uint_as_float(r[j + 2]) + (p.bias ? p.bias[n0 + c0 + j + 2] : 0.f);
+                o.w = __uint_as_float(r[j + 3]) + (p.bias ? p.bias[n0 + c0 + j + 3] : 0.f);
+                if (p.relu) {
+                  o.x = fmaxf(o.x, 0.f);
+                  o.y = fmaxf(o.y, 0.f);
+                  o.z = fmaxf(o.z, 0.f);
+                  o.w = fmaxf(o.w, 0.f);
+                }
+                *reinterpret_cast<float4*>(dst + j) = o;
               }
-              *reinterpret_cast<float4*>(dst + j) = o;
             }
+            continue;
           }
+          __syncwarp();   // the previous block's reads of the staging buffer are done
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 o;
+            o.x = __uint_as_float(r[j + 0]) + (p.bias ? p.bias[n0 + c0 + j + 0] : 0.f);
+            o.y = __uint_as_float(r[j + 1]) + (p.bias ? p.bias[n0 + c0 + j + 1] : 0.f);
+            o.z = __uint_as_float(r[j + 2]) + (p.bias ? p.bias[n0 + c0 + j + 2] : 0.f);
+            o.w = __uint_as_float(r[j + 3]) + (p.bias ? p.bias[n0 + c0 + j + 3] : 0.f);
+            if (p.relu) {
+              o.x = fmaxf(o.x, 0.f);
+              o.y = fmaxf(o.y, 0.f);
+              o.z = fmaxf(o.z, 0.f);
+              o.w = fmaxf(o.w, 0.f);
+            }
+            *reinterpret_cast<float4*>(stage_w + lane * 64 + ((((j >> 2) ^ (lane >> 1)) & 3) << 4)) = o;
+          }
+          __syncwarp();
+          if (tr) EFGB_TRACE(1000 + (c0 >> 4), 2);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int rl = (lane >> 2) + 8 * k;
+            const float4 o = *reinterpret_cast<const float4*>(stage_w + rl * 64 + (((lane ^ (rl >> 1)) & 3) << 4));
+            const int64_t row = row0 + rl;
+            if (row < p.num_out) *reinterpret_cast<float4*>(p.out + row * p.n_out + n0 + c0 + (lane & 3) * 4) = o;
+          }
+          if (tr) EFGB_TRACE(1000 + (c0 >> 4), 3);
         }
       }
       tc_fence_before();
       __syncwarp();
+      if (quarter == 0 && lane == 0) EFGB_TRACE(3 + 2 * i, 6);
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) EFGB_TRACE(0, 7);
   if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
@@ -1238,6 +1477,22 @@ static bool supported(int c_red, int n_out, int taps) {
 static int chunks_for(int taps, int c_red) { return (taps * c_red + kChunkK - 1) / kChunkK; }
 static int chunks_for_bf16(int taps, int c_red) { return (taps * c_red + kBf16ChunkK - 1) / kBf16ChunkK; }
 static bool supported_bf16(int c_red, int n_out, int taps) { return supported(c_red, n_out, taps) && c_red % 8 == 0; }
+// Depth of the A ring (128-row stages of `parts` operand images) and of the weight ring for n_cta output columns:
+// 227 KB minus barriers / alignment slack and the epilogue staging buffers.
+struct RingDepths {
+  int sa, sb;
+};
+static RingDepths ring_depths(int parts, int n_cta, bool staged = true) {
+  const int a_bytes = parts * kTileM * 128;
+  const int b_bytes = parts * n_cta * 128;
+  RingDepths d;
+  d.sb = b_bytes >= 65536 ? 2 : (b_bytes >= 16384 ? EFGB_TC_SB_MID : 4);
+  const int budget = 227 * 1024 - 2048 - (staged ? 4 * kEpiStageBytes : 0);
+  d.sa = (budget - d.sb * b_bytes) / a_bytes;
+  if (d.sa > 6) d.sa = 6;
+  return d;
+}
+
 static bool planes_supported(int c_red) { return c_red == 16 || c_red == 32 || (c_red >= 64 && c_red % 64 == 0); }
 
 // fp32 [rows, C] -> planes [rows][hi C x bf16 | lo C x bf16]: hi = bf16_rn(v), lo = bf16_rn(v - hi).  One thread per 8 values.
@@ -1347,6 +1602,7 @@ static int launch_forward(const float* in_feats, const void* planes, int64_t num
   p.bias = bias;
   p.relu = relu ? 1 : 0;
   p.nbr = nbr;
+  p.wide = (split == 2 && !planes && (reinterpret_cast<uintptr_t>(in_feats) & 31) == 0) ? 1 : 0;
   p.out = out_feats;
   p.num_out = num_out;
   p.c_red = c_red;
@@ -1354,13 +1610,31 @@ static int launch_forward(const float* in_feats, const void* planes, int64_t num
   p.n_out = n_out;
   p.chunks = split == 2 ? tc::chunks_for_bf16(taps, c_red) : tc::chunks_for(taps, c_red);
   p.num_tiles = static_cast<int>((num_out + tc::kTileM - 1) / tc::kTileM);
-  // N split: wide outputs (dense GEMMs) are cut into 256-column slabs over grid.y
+  // N split: wide outputs (dense GEMMs) are cut into column slabs over grid.y — as wide as leaves room for at least
+  // three A stages next to the weight ring and the epilogue staging (256 columns for one operand image, 128 for two)
+  const int parts = split ? 2 : 1;
+  const int a_bytes = parts * tc::kTileM * 128;
   int n_split = n_out > 256 ? n_out / 256 : 1;
   int n_cta = n_out / n_split;
+  // The epilogue's staging buffers do not fit next to a 256-column weight ring with two operand images.  Short
+  // reductions (K <= 512: the tile's epilogue is as long as its main loop) take 128-column CTAs with the coalescing
+  // epilogue; long ones keep the 256-column CTA (half the A production per output) and the row-per-thread stores, which
+  // their main loop hides.  Measured on 70 k x {256, 1024} token-wise linears, profiles/r2_dense_micro.txt.
+  p.epi_staged = 1;
+  if (tc::ring_depths(parts, n_cta).sa < 3) {
+    if (p.chunks > 8 && tc::ring_depths(parts, n_cta, false).sa >= 3) {
+      p.epi_staged = 0;
+    } else {
+      while (tc::ring_depths(parts, n_cta).sa < 3 && n_cta / 2 >= 32 && (n_cta / 2) % 16 == 0) {
+        n_split *= 2;
+        n_cta /= 2;
+      }
+    }
+  }
   // super-tile: T row tiles share each weight chunk (T * acc_cols fp32 columns per accumulator set, two sets in TMEM)
   auto acc_cols_of = [&](int n) { return (split != 0 && n <= 128) ? 2 * n : n; };
   int T = 256 / acc_cols_of(n_cta);
-  if (T > 8) T = 8;
+  if (T > EFGB_TC_MAX_T) T = EFGB_TC_MAX_T;
   if (T < 1) T = 1;
   // keep at least ~3/4 of the SMs busy; beyond that, sharing weight chunks across more tiles wins (the weight
   // stream from L2 is the bound for C >= 64)
@@ -1377,20 +1651,18 @@ static int launch_forward(const float* in_feats, const void* planes, int64_t num
   p.concat = p.acc_cols != n_cta ? 1 : 0;
   p.tiles_per_super = T;
   p.num_super = (p.num_tiles + T - 1) / T;
-  const int parts = split ? 2 : 1;
-  const int a_bytes = parts * tc::kTileM * 128;
   const int b_bytes = parts * n_cta * 128;
-  p.sb = b_bytes >= 65536 ? 2 : (b_bytes >= 16384 ? 3 : 4);
-  const int budget = 227 * 1024 - 2048;
-  p.sa = (budget - p.sb * b_bytes) / a_bytes;
-  if (p.sa > 6) p.sa = 6;
+  if (!p.epi_staged && tc::ring_depths(parts, n_cta).sa >= 3) p.epi_staged = 1;   // n_cta was halved after the choice
+  const tc::RingDepths depths = tc::ring_depths(parts, n_cta, p.epi_staged != 0);
+  p.sa = depths.sa;
+  p.sb = depths.sb;
   EFGB_REQUIRE(p.sa >= 2, EFGB_EINVAL, "spconv_tc_forward: tile does not fit shared memory");
   EFGB_REQUIRE(!planes || p.sa >= tc::kPlaneDepth + 2, EFGB_EINVAL, "spconv_tc_forward: A ring too shallow for the cp.async producers");
   p.cred_shift = -1;
   for (int sft = 2; sft < 16; ++sft)
     if ((1 << sft) == c_red) p.cred_shift = sft;
   const size_t smem = 1024 + static_cast<size_t>(p.sa) * a_bytes + static_cast<size_t>(p.sb) * b_bytes +
-                      (2 * p.sa + 2 * p.sb + 4) * 8 + 16;
+                      (2 * p.sa + 2 * p.sb + 4) * 8 + 32 + (p.epi_staged ? 4 * tc::kEpiStageBytes : 0);
   int gx = kNumSMs / n_split;
   if (gx < 1) gx = 1;
   if (gx > p.num_super) gx = p.num_super;
@@ -1415,13 +1687,21 @@ extern "C" int efgb_spconv_tc_forward_ex(const float* in_feats, int64_t num_in, 
   return launch_forward(in_feats, nullptr, num_in, c_red, packed, bias, nbr, num_out, taps, n_out, split, relu, out_feats, stream_);
 }
 
+#if EFGB_TC_TRACE
+extern "C" int efgb_debug_trace_read(long long* host, int stages) {
+  if (stages > tc::kTraceStages) stages = tc::kTraceStages;
+  EFGB_CUDA_OK(cudaDeviceSynchronize());
+  EFGB_CUDA_OK(cudaMemcpyFromSymbol(host, tc::g_trace, sizeof(long long) * 12 * stages));
+  return stages;
+}
+#endif
+
 extern "C" int efgb_spconv_tc_planes_supported(int c_red, int n_out, int taps) {
   if (!tc::supported_bf16(c_red, n_out, taps) || !tc::planes_supported(c_red)) return 0;
   // the cp.async producers need kPlaneDepth + 2 A stages next to the weight ring
-  const int n_cta = n_out > 256 ? 256 : n_out;
-  const int b_bytes = 2 * n_cta * 128;
-  const int sb = b_bytes >= 65536 ? 2 : (b_bytes >= 16384 ? 3 : 4);
-  return (227 * 1024 - 2048 - sb * b_bytes) / (2 * tc::kTileM * 128) >= tc::kPlaneDepth + 2 ? 1 : 0;
+  int n_cta = n_out > 256 ? 256 : n_out;
+  while (tc::ring_depths(2, n_cta).sa < 3 && n_cta / 2 >= 32 && (n_cta / 2) % 16 == 0) n_cta /= 2;
+  return tc::ring_depths(2, n_cta).sa >= tc::kPlaneDepth + 2 ? 1 : 0;
 }
 
 extern "C" int efgb_spconv_tc_forward_planes(const void* in_planes, int64_t num_in, int c_red, const float* packed,

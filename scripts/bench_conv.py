@@ -34,7 +34,7 @@ for mode in modes:
     ops.CONV_PRECISION = mode.split("-")[0]
     inline = mode.endswith("-inline")
     for lvl, c in zip(range(4), [16, 64, 128, 256]):
-        if str(lvl) not in os.environ.get("LEVELS", "0,1,2,3").split(","):
+        if str(lvl) not in os.environ.get("LEVELS", "0,1,2,3").split(",") or __name__ != "__main__":
             continue
         oc, od, nbr, nbr_s, nbr_t, m_in = levels[lvl]
         mo = oc.shape[0]
