@@ -60,6 +60,8 @@ def parse_args():
     ap.add_argument("--points", type=int, default=None)
     ap.add_argument("--scenes", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prefetch", action="store_true",
+                    help="voxelize / build rulebooks in line with the step instead of one batch ahead on a side stream")
     ap.add_argument("--no-graph", action="store_true",
                     help="keep the static section (FPN top-down, transformer, heads) eager instead of CUDA-graphed")
     ap.add_argument("--cpu-points", type=int, default=POINTS_PER_SCENE)
@@ -333,9 +335,12 @@ def run_efgb200(args, backend=None):
     h2d_bytes = sum(t.numel() * 4 for t, _ in pinned[0])
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    def step(batch):
+    def inputs_of(batch):
+        return [({"points": p}, {"annotations": a}) for p, a in batch]
+
+    def step(batch, prepared=None):
         averager.zero_grad()          # one memset per gradient bucket; p.grad are views into the buckets
-        losses = model([({"points": p}, {"annotations": a}) for p, a in batch])
+        losses = model(inputs_of(batch)) if prepared is None else model(inputs_of(batch), prepared=prepared)
         total = loss_total(losses)
         total.backward()              # bucket all-reduces are launched from inside backward (post-accumulate hooks)
         averager.finish()
@@ -343,32 +348,67 @@ def run_efgb200(args, backend=None):
         opt.step()
         return total
 
+    # Input pipeline: the index part of batch i + 1 (H2D copy of the points, voxelizer, the strided rulebooks — the
+    # only places that read a count back from the device) runs on its own high-priority stream while step i executes,
+    # so the training stream never synchronises and the host stays ahead of the GPU (model.prepare).
+    prefetch = backend is None and not args.no_prefetch and hasattr(model, "prepare")
+    prep_stream = torch.cuda.Stream(device=dev, priority=-1) if prefetch else None
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = []
+
     def timed(batches, steps, from_host, sampler=None):
         """EXACTLY `steps` steps between one pair of CUDA events, bracketed by barrier + synchronize on both sides.
         L2 is flushed before every step (a 256 MiB memset inside the timed span, ~0.04 ms).  With host inputs every
-        step copies its pinned point clouds to the device and reads its loss back (a full pipeline drain per step)."""
+        step copies its pinned point clouds to the device and reads its loss back: the read of step i is an
+        asynchronous copy into pinned memory that the host waits for while step i + 1 is in flight (every read
+        completes inside the timed span)."""
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         last = None
+        back = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(2)]   # [loss, matcher status]
+        back_ev = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def read_back(i):
+            back_ev[i & 1].synchronize()
+            if back[i & 1][1] != 0:
+                raise ValueError("matrix contains invalid numeric entries (device linear_sum_assignment)")
+            return float(back[i & 1][0])
+
         barrier()
         if sampler is not None:
             sampler.start()
         ev0.record()
+        host_t0 = time.perf_counter()
+        prepared = None
         for i in range(steps):
             l2_flush.zero_()
             b = batches[i % len(batches)]
+            if prefetch:
+                if prepared is None:
+                    prepared = model.prepare(inputs_of(b), prep_stream)   # first step of the span
+                total = step(b, prepared)
+                prepared = model.prepare(inputs_of(batches[(i + 1) % len(batches)]), prep_stream) if i + 1 < steps else None
+            else:
+                if from_host:
+                    b = [(t.to(dev, non_blocking=True), a) for t, a in b]
+                total = step(b)
             if from_host:
-                b = [(t.to(dev, non_blocking=True), a) for t, a in b]
-            total = step(b)
-            if from_host:
-                last = float(total.item())  # D2H read of the step's result
-                if backend is None:
-                    ops.lsa_status()        # the host is synchronised here anyway: surface an infeasible matching as scipy would
+                # D2H read of the step's result, one step behind the launches
+                back[i & 1][0:1].copy_(total.detach().reshape(1), non_blocking=True)
+                status = ops.lsa_status_tensor(dev) if backend is None else None
+                if status is not None:
+                    back[i & 1][1:2].copy_(status.reshape(1).float(), non_blocking=True)
+                back_ev[i & 1].record()
+                if i >= 1:
+                    last = read_back(i - 1)
+        if from_host and steps > 0:
+            last = read_back(steps - 1)
         ev1.record()
+        host_ms.append((time.perf_counter() - host_t0) * 1e3 / max(steps, 1))   # host enqueue time per step
         if sampler is not None:
             sampler.stop()  # the device is still executing the tail of the last step
         barrier()
@@ -458,10 +498,14 @@ def run_efgb200(args, backend=None):
                    "grid": "x".join(str(int(g)) for g in spec.grid_size), "step": "voxelize+fwd+bwd+allreduce+adamw",
                    "conv_precision": ops.CONV_PRECISION if backend is None else "fp32 torch ops",
                    "cuda_graph": graph_state, "parallelism": "dp%d" % world,
+                   "input_pipeline": ("index part of the next batch (H2D, voxelizer, strided rulebooks) on a side stream during "
+                                      "the current step; e2e loss read back asynchronously, one step behind") if prefetch else
+                                     "in line (no prefetch)",
                    "l2": "flushed before every timed step (256 MiB memset, inside the timed span)"},
         "e2e": {"value": round(e2e_value, 3), "unit": "scenes/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": last_loss},
         "gpu_launches": int(launches),
+        "host_enqueue_ms_per_step": round(host_ms[0], 3),   # Python + launch time of a step (no synchronisation inside)
         "clocks": clocks,
     }
     if backend is None:

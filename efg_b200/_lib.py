@@ -42,6 +42,8 @@ SIGNATURES = {
     "efgb_spconv_tc_supported": (_int, [_int, _int, _int]),
     "efgb_spconv_tc_packed_bytes": (_sz, [_int, _int, _int, _int]),
     "efgb_spconv_tc_pack": (_int, [_vp, _int, _int, _int, _int, _int, _vp, _vp]),
+    "efgb_spconv_tc_pack_blocks": (_i64, [_int, _int, _int, _int]),
+    "efgb_spconv_tc_pack_batched": (_int, [_vp, _int, _i64, _vp]),
     "efgb_spconv_tc_forward": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp]),
     "efgb_split_bf16": (_int, [_vp, _i64, _int, _vp, _vp]),
     "efgb_spconv_tc_planes_supported": (_int, [_int, _int, _int]),

@@ -1061,12 +1061,8 @@ pack_weights_kernel(const float* __restrict__ w, int c_out, int taps, int c_in, 
 
 
 // bf16x3 weight image: [chunk of 64 K-values][hi | lo][n][64 bf16], K-major, 128-byte swizzle (16-byte pieces of 8 values).
-__global__ void __launch_bounds__(256)
-pack_weights_bf16_kernel(const float* __restrict__ w, int c_out, int taps, int c_in, int mode, int n_out, int c_red, int chunks,
-                         __nv_bfloat16* __restrict__ packed) {
-  const int64_t total = static_cast<int64_t>(chunks) * n_out * kBf16ChunkK;
-  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (t >= total) return;
+__device__ __forceinline__ void pack_bf16_element(const float* __restrict__ w, int c_out, int taps, int c_in, int mode, int n_out,
+                                                  int c_red, int64_t t, __nv_bfloat16* __restrict__ packed) {
   const int kk = static_cast<int>(t % kBf16ChunkK);
   const int n = static_cast<int>((t / kBf16ChunkK) % n_out);
   const int chunk = static_cast<int>(t / (static_cast<int64_t>(kBf16ChunkK) * n_out));
@@ -1088,6 +1084,37 @@ pack_weights_bf16_kernel(const float* __restrict__ w, int c_out, int taps, int c
   const __nv_bfloat16 hi = __float2bfloat16_rn(v);
   base[off] = hi;
   base[static_cast<int64_t>(n_out) * kBf16ChunkK + off] = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+__global__ void __launch_bounds__(256)
+pack_weights_bf16_kernel(const float* __restrict__ w, int c_out, int taps, int c_in, int mode, int n_out, int c_red, int chunks,
+                         __nv_bfloat16* __restrict__ packed) {
+  const int64_t total = static_cast<int64_t>(chunks) * n_out * kBf16ChunkK;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  pack_bf16_element(w, c_out, taps, c_in, mode, n_out, c_red, t, packed);
+}
+
+// Every bf16x3 weight image of a training step in ONE launch.  jobs[j] = {weights, image, c_out, taps, c_in, mode,
+// first block, blocks} as eight int64; a block finds its job by bisection over the first-block column.
+__global__ void __launch_bounds__(256) pack_weights_bf16_batched_kernel(const int64_t* __restrict__ jobs, int n_jobs) {
+  int lo = 0, hi = n_jobs - 1;
+  const int64_t b = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(jobs + mid * 8 + 6) <= b) lo = mid; else hi = mid - 1;
+  }
+  const int64_t* j = jobs + lo * 8;
+  const float* w = reinterpret_cast<const float*>(__ldg(j + 0));
+  __nv_bfloat16* packed = reinterpret_cast<__nv_bfloat16*>(__ldg(j + 1));
+  const int c_out = static_cast<int>(__ldg(j + 2)), taps = static_cast<int>(__ldg(j + 3)), c_in = static_cast<int>(__ldg(j + 4));
+  const int mode = static_cast<int>(__ldg(j + 5));
+  const int n_out = mode == 0 ? c_out : c_in;
+  const int c_red = mode == 0 ? c_in : c_out;
+  const int64_t total = static_cast<int64_t>((taps * c_red + kBf16ChunkK - 1) / kBf16ChunkK) * n_out * kBf16ChunkK;
+  const int64_t t = (b - __ldg(j + 6)) * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  pack_bf16_element(w, c_out, taps, c_in, mode, n_out, c_red, t, packed);
 }
 
 // ================================================================================================
@@ -1561,6 +1588,23 @@ extern "C" int efgb_spconv_tc_pack(const float* w_param, int c_out, int taps, in
   else
     tc::pack_weights_kernel<false><<<nb, 256, 0, stream>>>(w_param, c_out, taps, c_in, mode, n_out, c_red, chunks, packed);
   EFGB_LAUNCH_OK("pack_weights_kernel");
+  return EFGB_OK;
+}
+
+extern "C" int64_t efgb_spconv_tc_pack_blocks(int c_out, int taps, int c_in, int mode) {
+  const int n_out = mode == 0 ? c_out : c_in;
+  const int c_red = mode == 0 ? c_in : c_out;
+  if (mode < 0 || mode > 2 || !tc::supported_bf16(c_red, n_out, taps)) return 0;
+  return (static_cast<int64_t>(tc::chunks_for_bf16(taps, c_red)) * n_out * tc::kBf16ChunkK + 255) / 256;
+}
+
+extern "C" int efgb_spconv_tc_pack_batched(const int64_t* jobs, int n_jobs, int64_t total_blocks, efgb_stream_t stream_) {
+  cudaStream_t stream = as_stream(stream_);
+  EFGB_REQUIRE(n_jobs >= 0 && total_blocks >= 0 && total_blocks < (1ll << 31), EFGB_EINVAL, "spconv_tc_pack_batched: bad argument");
+  if (n_jobs == 0 || total_blocks == 0) return EFGB_OK;
+  EFGB_REQUIRE(jobs != nullptr, EFGB_EINVAL, "spconv_tc_pack_batched: null job table");
+  tc::pack_weights_bf16_batched_kernel<<<static_cast<unsigned>(total_blocks), 256, 0, stream>>>(jobs, n_jobs);
+  EFGB_LAUNCH_OK("pack_weights_bf16_batched_kernel");
   return EFGB_OK;
 }
 

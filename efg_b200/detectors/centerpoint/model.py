@@ -72,6 +72,8 @@ class VoxelNet(nn.Module):
         return targets
 
     def forward(self, batched_inputs):
+        if self.training and self.device.type == "cuda":
+            ops.refresh_packs()   # every weight image the optimizer step made stale, in one launch
         samples = [bi[0] for bi in batched_inputs]
         infos = [bi[1] for bi in batched_inputs]
         batch_size = len(samples)

@@ -12,6 +12,7 @@ import torch
 from torch import nn
 from torch.nn import functional as F
 
+from ... import ops
 from ..voxel_detr.losses import MatchIndex, TargetList, device_matches, upload_matches
 from ..voxel_detr.model import VoxelDETR
 from ..voxel_detr.transformer import Transformer
@@ -91,6 +92,8 @@ class ConQueR(VoxelDETR):
                                   mom=config.model.contrastive.mom)
 
     def forward(self, batched_inputs):
+        if self.training and self.device.type == "cuda":
+            ops.refresh_packs()   # every weight image the optimizer step made stale, in one launch
         targets = self.encode_targets(batched_inputs) if self.training else None
         if targets is not None:
             self.transformer.proposal_head.losses.request_normaliser(targets, self.device)

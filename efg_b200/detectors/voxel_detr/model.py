@@ -187,8 +187,12 @@ class VoxelDETR(nn.Module):
         targets.labels_cat, targets.boxes_cat, targets.offsets = labels, boxes, offsets
         return targets
 
-    def extract(self, batched_inputs):
+    def extract(self, batched_inputs, prepared=None):
         batch_size = len(batched_inputs)
+        if prepared is not None:
+            feats = self.backbone.extractor.forward_dense(self.bottom_up_maps(batched_inputs, prepared))
+            feats_pos = [(feats[f], self.backbone.position_encoding(feats[f]).type_as(feats[f])) for f in self.backbone.out_features]
+            return [self.input_proj[i](fp[0]) for i, fp in enumerate(feats_pos)], [fp[1] for fp in feats_pos]
         samples = [bi[0] for bi in batched_inputs]
         if "voxels" in samples[0]:
             voxels, coords, npv, input_shape = collate_voxels(samples, self.device)
@@ -199,10 +203,52 @@ class VoxelDETR(nn.Module):
         return features, [fp[1] for fp in feats_pos]
 
     # ---------------------------------------------------------------------------------------
-    def bottom_up_maps(self, batched_inputs):
+    def prepare(self, batched_inputs, stream=None):
+        """The index part of a step for raw-point samples, without features or parameters: host-to-device copy of the
+        points, voxelizer (+ mean VFE) and every strided rulebook of the sparse backbone.  These are the only places of
+        a training step that read a count back from the device; a loader calls this for batch i + 1 on its own (high
+        priority) stream while step i runs, and passes the result to forward(..., prepared=...), which then never
+        synchronises: the host runs ahead of the GPU instead of draining it once per downsampling."""
+        samples = [bi[0] for bi in batched_inputs]
+        if "voxels" in samples[0] or self.device.type != "cuda":
+            return None
+        bottom_up = self.backbone.extractor.bottom_up
+        if not hasattr(bottom_up, "plan_geometry"):
+            return None
+        stream = stream or torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(stream):
+            voxels, coords, npv, input_shape = self.voxelize_on_device(samples)
+            indice_dict = bottom_up.plan_geometry(coords, len(batched_inputs), input_shape)
+            done = torch.cuda.Event()
+            done.record(stream)
+        return {"voxels": voxels, "coords": coords, "npv": npv, "input_shape": input_shape, "indice_dict": indice_dict,
+                "done": done, "stream": stream, "batch_size": len(batched_inputs)}
+
+    @staticmethod
+    def _adopt(prepared):
+        """Make the tensors of prepare() safe to use on the current stream: order after the producer stream and tell
+        the caching allocator about the second stream."""
+        cur = torch.cuda.current_stream()
+        if prepared["stream"] == cur:
+            return
+        cur.wait_event(prepared["done"])
+        tensors = [prepared["voxels"], prepared["coords"], prepared["npv"]]
+        for rb in prepared["indice_dict"].values():
+            tensors += [t for t in (rb.nbr, rb.nbr_t, rb.out_indices) if isinstance(t, torch.Tensor)]
+        for t in tensors:
+            t.record_stream(cur)
+        prepared["stream"] = cur
+
+    def bottom_up_maps(self, batched_inputs, prepared=None):
         """Voxelize + sparse backbone: the dense bottom-up feature maps the FPN needs (dynamic shapes end here)."""
         batch_size = len(batched_inputs)
         samples = [bi[0] for bi in batched_inputs]
+        if prepared is not None:
+            assert prepared["batch_size"] == batch_size
+            self._adopt(prepared)
+            voxels, coords, npv, input_shape = (prepared[k] for k in ("voxels", "coords", "npv", "input_shape"))
+            encoded = self.backbone.reader(voxels, npv, coords)
+            return self.backbone.extractor.bottom_up(encoded, coords, batch_size, input_shape, indice_dict=prepared["indice_dict"])
         if "voxels" in samples[0]:
             voxels, coords, npv, input_shape = collate_voxels(samples, self.device)
         else:
@@ -224,7 +270,14 @@ class VoxelDETR(nn.Module):
             section = _StaticSection(self, names)
             sample = tuple(feats[n].detach().clone().requires_grad_(True) for n in names)
             torch.cuda.synchronize()
-            self._static_call = torch.cuda.make_graphed_callables(section, sample, allow_unused_input=True)
+            # weight images: the captured kernels read the cached images, which forward() refreshes in one launch
+            # before every replay (ops.refresh_packs) instead of one captured pack kernel per layer and direction
+            ops.PACKS_REFRESHED_PER_STEP = True
+            try:
+                self._static_call = torch.cuda.make_graphed_callables(section, sample, allow_unused_input=True)
+            finally:
+                ops.PACKS_REFRESHED_PER_STEP = False
+            self._static_packs = ops.pin_pack_cache()   # the graphs hold raw pointers into these images
             self._static_names, self._static_batch = names, len(batched_inputs)
             self._static_section = [section]
             return True
@@ -233,18 +286,21 @@ class VoxelDETR(nn.Module):
             self.static_graph_error = "%s: %s" % (type(e).__name__, e)
             return False
 
-    def forward(self, batched_inputs):
+    def forward(self, batched_inputs, prepared=None):
+        """`prepared`: the result of prepare(batched_inputs) (optional; see there)."""
+        if self.training and self.device.type == "cuda":
+            ops.refresh_packs()   # every weight image the optimizer step made stale, in one launch
         targets = self.encode_targets(batched_inputs) if self.training else None
         if targets is not None:
             # the loss normaliser depends on the targets only: its all-reduce runs under the forward pass
             self.transformer.proposal_head.losses.request_normaliser(targets, self.device)
         call = getattr(self, "_static_call", None)
         if call is not None and self.training and torch.is_grad_enabled() and len(batched_inputs) == self._static_batch:
-            feats = self.bottom_up_maps(batched_inputs)
+            feats = self.bottom_up_maps(batched_inputs, prepared)
             cls_out, box_out, memory, anchors, topk_idx, enc_cls, enc_box = call(*[feats[n] for n in self._static_names])
             self.transformer._enc_head_out = (enc_cls, enc_box)
             return self.losses(cls_out, box_out, memory, anchors, topk_idx, targets)
-        features, pos = self.extract(batched_inputs)
+        features, pos = self.extract(batched_inputs, prepared)
         hs, init_ref, inter_refs, memory, anchors, topk_idx = self.transformer(features, pos)
 
         head = self.transformer.decoder.detection_head

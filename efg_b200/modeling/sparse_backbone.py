@@ -136,10 +136,23 @@ class SparseResNet(nn.Module):
             self._out_feature_channels[f] *= multipliers[idx]
         self.compute_features = None  # None = all of out_features (reference behaviour)
 
-    def forward(self, voxel_features, coors, batch_size, input_shape):
+    def plan_geometry(self, coors, batch_size, input_shape):
+        """Every strided rulebook of the forward pass for these voxel coordinates, WITHOUT features: the part of the
+        pass that needs host reads (one output count per downsampling).  Returns the indice_dict to hand to forward();
+        a data pipeline runs this one batch ahead on its own stream so that the feature pass never synchronises."""
         sp = self._sp[0]
         sparse_shape = np.array(input_shape[::-1]) + [1, 0, 0]
-        x = sp.SparseConvTensor(voxel_features, coors.int(), sparse_shape, batch_size)
+        x = sp.SparseConvTensor(None, coors.int(), sparse_shape, batch_size)
+        wanted = self._out_features if self.compute_features is None else \
+            [f for f in self._out_features if f in self.compute_features]
+        self._plan_rulebooks(x, wanted)
+        return x.indice_dict
+
+    def forward(self, voxel_features, coors, batch_size, input_shape, indice_dict=None):
+        sp = self._sp[0]
+        sparse_shape = np.array(input_shape[::-1]) + [1, 0, 0]
+        kw = {} if indice_dict is None else {"indice_dict": indice_dict}   # rulebooks planned ahead (plan_geometry)
+        x = sp.SparseConvTensor(voxel_features, coors.int(), sparse_shape, batch_size, **kw)
         wanted = self._out_features if self.compute_features is None else \
             [f for f in self._out_features if f in self.compute_features]
         self._plan_rulebooks(x, wanted)

@@ -357,8 +357,12 @@ def spconv_tc(feats, w_param, bias, nbr, mode, relu=False, planes=None):
 # Packed weight images, cached per (parameter storage, version, mode, split): a parameter changes once per optimizer
 # step, so forward and dgrad of a layer and every micro-batch in between reuse the image (round 1 repacked on every
 # call: 82 pack launches per step).  Tensor._version increments on every in-place update (optimizer.step, load_state_dict).
-_PACK_CACHE = {}
+# refresh_packs() re-packs every stale bf16x3 image of the cache in ONE launch; a training loop (the model's forward)
+# calls it once per step, after which the per-layer lookups below are hits.
+_PACK_CACHE = {}       # key -> [version, packed image, weakref(base parameter), weight view]
 _PACK_CACHE_MAX = 512
+_PACK_JOBS = {}        # tuple of stale keys -> (device job table, total blocks)
+PACKS_REFRESHED_PER_STEP = False   # set by a training loop that calls refresh_packs() before every forward (see below)
 
 
 def packed_weights(w_param, mode, split):
@@ -369,26 +373,91 @@ def packed_weights(w_param, mode, split):
     ver = base._version
     hit = _PACK_CACHE.get(key)
     capturing = torch.cuda.is_current_stream_capturing()
-    if hit is not None and hit[0] == ver and hit[2]() is base and not capturing:   # same tensor object, not updated since
-        return hit[1]   # (under stream capture the pack kernel must be part of the graph: replays read the live weights)
+    same = hit is not None and hit[2]() is base
+    if same and hit[0] == ver:   # same tensor object, not updated since
+        # Under stream capture a cached image is only valid if something refreshes it before every replay: the
+        # refresh_packs() protocol.  Without it the pack kernel has to be part of the graph (replays read the live weights).
+        if not capturing or PACKS_REFRESHED_PER_STEP:
+            return hit[1]
     L = _lib.lib()
-    packed = torch.empty(L.efgb_spconv_tc_packed_bytes(taps, c_red, n_out, split) // 4, dtype=torch.float32, device=w_param.device)
+    if same and not capturing:
+        packed = hit[1]   # stale image: re-pack in place (refresh_packs() job tables hold its address)
+    else:
+        packed = torch.empty(L.efgb_spconv_tc_packed_bytes(taps, c_red, n_out, split) // 4, dtype=torch.float32,
+                             device=w_param.device)
     t0 = PROFILER.begin() if PROFILER is not None else None
     _lib.check(L.efgb_spconv_tc_pack(_p(w_param), c_out, taps, c_in, mode, split, _p(packed), _stream()), "spconv_tc_pack")
     if t0 is not None:
         PROFILER.end("spconv_pack_weights", t0, 4 * (w_param.numel() + packed.numel()))
     if capturing:
         return packed   # lives in the graph's memory pool; never handed to eager callers
+    if same:
+        hit[0] = ver
+        return packed
     if len(_PACK_CACHE) >= _PACK_CACHE_MAX:
-        _PACK_CACHE.clear()
-    _PACK_CACHE[key] = (ver, packed, weakref.ref(base))
+        clear_pack_cache()
+    _PACK_JOBS.clear()   # the key may have had another image
+    _PACK_CACHE[key] = [ver, packed, weakref.ref(base), w_param.detach()]
     return packed
+
+
+def refresh_packs():
+    """Re-pack, in one launch, every cached bf16x3 weight image whose parameter has been updated since it was packed
+    (after optimizer.step: all of them).  Returns the number of images refreshed.  With PACKS_REFRESHED_PER_STEP set,
+    CUDA-graph captures reuse the cached images instead of recording one pack kernel per layer — the caller then owes
+    a refresh_packs() before every replay."""
+    stale = []
+    for key, hit in list(_PACK_CACHE.items()):
+        base = hit[2]()
+        if base is None:
+            del _PACK_CACHE[key]
+        elif key[3] == 2 and base._version != hit[0]:
+            stale.append(key)
+    if len(stale) < 2:
+        return 0   # a single image: the per-layer path packs it on use
+    L = _lib.lib()
+    sig = tuple(stale)
+    jobs = _PACK_JOBS.get(sig)
+    if jobs is None:
+        rows, first = [], 0
+        for key in stale:
+            c_out, taps, c_in = key[1]
+            blocks = int(L.efgb_spconv_tc_pack_blocks(c_out, taps, c_in, key[2]))
+            rows.append([key[0], _PACK_CACHE[key][1].data_ptr(), c_out, taps, c_in, key[2], first, blocks])
+            first += blocks
+        if len(_PACK_JOBS) > 8:
+            _PACK_JOBS.clear()
+        table = torch.tensor(rows, dtype=torch.int64)
+        dev = torch.device("cuda", stale[0][4])
+        jobs = _PACK_JOBS[sig] = (table.pin_memory().to(dev, non_blocking=True), first)
+    t0 = PROFILER.begin() if PROFILER is not None else None
+    _lib.check(L.efgb_spconv_tc_pack_batched(_p(jobs[0]), len(stale), jobs[1], _stream()), "spconv_tc_pack_batched")
+    if t0 is not None:
+        PROFILER.end("spconv_pack_weights", t0, 0)
+    for key in stale:
+        hit = _PACK_CACHE[key]
+        hit[0] = hit[2]()._version
+    return len(stale)
 
 
 def clear_pack_cache():
     """Drop every cached weight image (needed only after writing a weight through `.data`, which bypasses the
     version counter the cache is keyed on)."""
+    if _PACK_PINNED:
+        raise RuntimeError("the weight-image cache is referenced by captured CUDA graphs (pin_pack_cache) and cannot be dropped")
     _PACK_CACHE.clear()
+    _PACK_JOBS.clear()
+
+
+_PACK_PINNED = []
+
+
+def pin_pack_cache():
+    """Called after capturing CUDA graphs under PACKS_REFRESHED_PER_STEP: the graphs read the cached images through raw
+    pointers, so the cache may no longer drop or replace them.  Returns the images (keep them referenced)."""
+    images = [hit[1] for hit in _PACK_CACHE.values()]
+    _PACK_PINNED.append(len(images))
+    return images
 
 
 def spconv_tc_wgrad_supported(c_in, c_out, taps):
@@ -449,6 +518,13 @@ def lsa_status(device=None, clear=True):
         status.zero_()
     if bad:
         raise ValueError("matrix contains invalid numeric entries (device linear_sum_assignment)")
+
+
+def lsa_status_tensor(device=None):
+    """The device flag lsa_status() reads (int32 scalar, or None before the first solve): a loop that reads its loss back
+    asynchronously copies this next to it instead of synchronising."""
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    return _LSA_STATUS.get(idx)
 
 
 def lsa_batched(mats):

@@ -166,6 +166,11 @@ int efgb_spconv_tc_supported(int c_red, int n_out, int taps);
 size_t efgb_spconv_tc_packed_bytes(int taps, int c_red, int n_out, int split);
 int efgb_spconv_tc_pack(const float* w_param, int c_out, int taps, int c_in, int mode, int split,
                         float* packed, efgb_stream_t stream);
+/* All bf16x3 (split = 2) weight images of a training step in one launch.  `jobs` is a DEVICE table of n_jobs rows of
+ * eight int64: {w_param pointer, packed pointer, c_out, taps, c_in, mode, first block, blocks}; blocks =
+ * efgb_spconv_tc_pack_blocks(...) (0: shape not supported), first block = running sum, total_blocks = the sum. */
+int64_t efgb_spconv_tc_pack_blocks(int c_out, int taps, int c_in, int mode);
+int efgb_spconv_tc_pack_batched(const int64_t* jobs, int n_jobs, int64_t total_blocks, efgb_stream_t stream);
 int efgb_spconv_tc_forward(const float* in_feats, int64_t num_in, int c_red, const float* packed,
                            const float* bias /* nullable [n_out] */, const int32_t* nbr,
                            int64_t num_out, int taps, int n_out, int split, float* out_feats,

@@ -240,3 +240,40 @@ def test_centerpoint_train_losses_parity():
     gc = dict(cpu.named_parameters())["center_head.tasks.0.hm.3.weight"].grad
     gg = dict(gpu.named_parameters())["center_head.tasks.0.hm.3.weight"].grad
     assert (gg.cpu() - gc).abs().max().item() < 1e-3 * max(1.0, gc.abs().max().item())
+
+
+def test_prepared_geometry_gives_the_same_step():
+    """VoxelDETR.prepare(): voxelizer + strided rulebooks built ahead on another stream; forward(prepared=...) must give
+    the losses and gradients of the in-line path, and must not build any strided rulebook itself."""
+    from efg_b200 import ops
+
+    _, gpu = _models()
+    gpu.train()
+    scenes = small_batch(2, 6000, seed=5)
+    inputs = [({"points": torch.from_numpy(p).cuda()}, {"annotations": a}) for p, a in scenes]
+    torch.manual_seed(1)
+    plain = gpu(inputs)
+    sum(v for k, v in plain.items() if k.startswith("loss")).backward()
+    g_plain = {n: p.grad.clone() for n, p in gpu.named_parameters() if p.grad is not None}
+    gpu.zero_grad(set_to_none=True)
+
+    side = torch.cuda.Stream(priority=-1)
+    prepared = gpu.prepare(inputs, side)
+    assert prepared is not None and len(prepared["indice_dict"]) >= 3
+    calls = []
+    real = ops.sparse_rulebook
+    ops.sparse_rulebook = lambda *a, **k: calls.append(1) or real(*a, **k)
+    try:
+        torch.manual_seed(1)
+        ahead = gpu(inputs, prepared=prepared)
+    finally:
+        ops.sparse_rulebook = real
+    assert not calls, "the prepared step built %d strided rulebooks in line" % len(calls)
+    assert set(ahead) == set(plain)
+    for k in plain:
+        assert torch.allclose(ahead[k], plain[k], rtol=1e-5, atol=1e-6), (k, float(ahead[k]), float(plain[k]))
+    sum(v for k, v in ahead.items() if k.startswith("loss")).backward()
+    for n, p in gpu.named_parameters():
+        if n in g_plain:
+            scale = float(g_plain[n].abs().max()) + 1e-12
+            assert float((p.grad - g_plain[n]).abs().max()) / scale < 5e-3, n   # atomics in the attention backward

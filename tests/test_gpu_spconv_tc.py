@@ -167,3 +167,39 @@ def test_dense_linear_on_tensor_cores_vs_torch_fp64(precision, cin, cout):
     assert (xg.grad.double() - xd.grad).abs().max().item() < 2e-4 * max(1.0, xd.grad.abs().max().item())
     assert (lin.weight.grad.double() - wd.grad).abs().max().item() < 5e-4 * max(1.0, wd.grad.abs().max().item())
     assert (lin.bias.grad.double() - bd.grad).abs().max().item() < 1e-3 * max(1.0, bd.grad.abs().max().item())
+
+
+def test_refresh_packs_repacks_every_stale_image_in_one_launch(precision):
+    """ops.refresh_packs(): after an in-place update of the parameters (optimizer.step) one batched launch brings every
+    cached bf16x3 weight image to what the per-layer pack produces, for forward and both dgrad layouts."""
+    ops = precision
+    ops.CONV_PRECISION = "bf16x3"
+    ops.clear_pack_cache()
+    torch.manual_seed(5)
+    shapes = [(16, 27, 16), (64, 27, 32), (128, 27, 128), (256, 1, 256), (1024, 1, 256), (32, 8, 16)]
+    params = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
+    modes = [0, 1, 2]
+    cached = {}
+    for p in params:
+        for mode in modes:
+            if mode == 2 and p.shape[1] == 1:
+                continue
+            cached[(id(p), mode)] = ops.packed_weights(p, mode, 2)
+    assert ops.refresh_packs() == 0          # nothing stale
+    with torch.no_grad():
+        for p in params:
+            p.mul_(1.5).add_(0.25)           # bumps Tensor._version
+    n = ops.refresh_packs()
+    assert n == len(cached)
+    before = {k: v.clone() for k, v in cached.items()}
+    for p in params:
+        for mode in modes:
+            if (id(p), mode) not in cached:
+                continue
+            again = ops.packed_weights(p, mode, 2)
+            assert again.data_ptr() == cached[(id(p), mode)].data_ptr()      # a hit: refreshed in place
+            fresh = torch.empty_like(again)
+            c_out, taps, c_in = p.shape
+            ops._lib.check(ops._lib.lib().efgb_spconv_tc_pack(ops._p(p), c_out, taps, c_in, mode, 2, ops._p(fresh), ops._stream()), "pack")
+            assert torch.equal(before[(id(p), mode)].view(torch.int32), fresh.view(torch.int32)), (tuple(p.shape), mode)
+    ops.clear_pack_cache()
