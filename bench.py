@@ -426,10 +426,11 @@ def run_efgb200(args, backend=None):
     # CUDA graphs for the static-shape section of the step (FPN top-down, encoder, decoder, heads; forward + backward)
     graph_state = "none"
     if backend is None and not args.no_graph and not args.profile_step and hasattr(model, "enable_static_graph"):
-        if args.workload == "voxel_detr":
+        if args.workload in ("voxel_detr", "centerpoint_waymo", "centerpoint_nusc"):
             ok = model.enable_static_graph([({"points": p}, {"annotations": a}) for p, a in resident[0]])
-            graph_state = "static section (FPN top-down + transformer + heads), forward and backward" if ok else \
-                "none (capture failed: %s)" % model.static_graph_error
+            what = "static section (FPN top-down + transformer + heads), forward and backward" if args.workload == "voxel_detr" \
+                else "static section (RPN neck + centre heads + losses), forward and backward"
+            graph_state = what if ok else "none (capture failed: %s)" % model.static_graph_error
             if not ok:
                 sys.stderr.write("bench.py: CUDA graph capture failed, running eagerly: %s\n" % model.static_graph_error)
             for i in range(3):

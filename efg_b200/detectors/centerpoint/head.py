@@ -91,6 +91,15 @@ class CenterHead(nn.Module):
         x = self.shared_conv(x)
         return [task(x) for task in self.tasks]
 
+    def _code_weights_on(self, like):
+        """code_weights as a tensor on `like`'s device, built once (a per-call new_tensor is a pageable host-to-device
+        copy: a synchronisation, and illegal under CUDA-graph capture)."""
+        cached = getattr(self, "_code_weights_cache", None)
+        if cached is None or cached.device != like.device or cached.dtype != like.dtype:
+            cached = torch.tensor(list(self.code_weights), dtype=like.dtype, device=like.device)
+            self._code_weights_cache = cached
+        return cached
+
     def loss(self, example, preds_dicts):
         out = {}
         for task_id, preds in enumerate(preds_dicts):
@@ -104,7 +113,7 @@ class CenterHead(nn.Module):
                 anno = torch.cat((preds["reg"], preds["height"], preds["dim"], preds["rot"]), dim=1)
                 target_box = torch.cat((target_box[..., :6], target_box[..., 8:]), dim=-1)  # drop the velocity target
             box_loss = self.criterion_reg(anno, example["mask"][task_id], example["ind"][task_id], target_box)
-            loc_loss = (box_loss * box_loss.new_tensor(self.code_weights[:box_loss.shape[0]])).sum()
+            loc_loss = (box_loss * self._code_weights_on(box_loss)[:box_loss.shape[0]]).sum()
             out["%d_loss" % task_id] = hm_loss + self.weight * loc_loss
             out["%d_hm_loss" % task_id] = hm_loss.detach()
             out["%d_loc_loss" % task_id] = loc_loss

@@ -71,26 +71,128 @@ class VoxelNet(nn.Module):
                 targets[key].append(arr.to(self.device, non_blocking=True))
         return targets
 
-    def forward(self, batched_inputs):
-        if self.training and self.device.type == "cuda":
-            ops.refresh_packs()   # every weight image the optimizer step made stale, in one launch
+    # ---------------------------------------------------------------------------------------
+    _TARGET_KEYS = ("hm", "anno_box", "ind", "mask", "cat")
+
+    def prepare(self, batched_inputs, stream=None):
+        """The index part of a training step for raw-point samples (see VoxelDETR.prepare): host-to-device copy of the
+        points, voxelizer (+ mean VFE), the strided rulebooks of the sparse encoder and the label assignment — everything
+        without parameters, including the only device-to-host reads of a step.  Run it for batch i + 1 on a side stream
+        while step i executes and pass the result to forward(..., prepared=...)."""
         samples = [bi[0] for bi in batched_inputs]
-        infos = [bi[1] for bi in batched_inputs]
+        if "voxels" in samples[0] or self.device.type != "cuda" or not hasattr(self.backbone, "plan_geometry"):
+            return None
+        stream = stream or torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(stream), torch.no_grad():
+            voxels, coords, npv, input_shape = self.voxelize_on_device(samples)
+            indice_dict = self.backbone.plan_geometry(coords, len(batched_inputs), input_shape)
+            if indice_dict is None:
+                return None
+            targets = self.label_assign([bi[1] for bi in batched_inputs]) if self.training else None
+            done = torch.cuda.Event()
+            done.record(stream)
+        return {"voxels": voxels, "coords": coords, "npv": npv, "input_shape": input_shape, "indice_dict": indice_dict,
+                "targets": targets, "done": done, "stream": stream, "batch_size": len(batched_inputs)}
+
+    @staticmethod
+    def _adopt(prepared):
+        cur = torch.cuda.current_stream()
+        if prepared["stream"] == cur:
+            return
+        cur.wait_event(prepared["done"])
+        tensors = [prepared["voxels"], prepared["coords"], prepared["npv"]]
+        for rb in prepared["indice_dict"].values():
+            tensors += [t for t in (rb.nbr, rb.nbr_t, rb.out_indices) if isinstance(t, torch.Tensor)]
+        if prepared["targets"] is not None:
+            for vals in prepared["targets"].values():
+                tensors += list(vals)
+        for t in tensors:
+            t.record_stream(cur)
+        prepared["stream"] = cur
+
+    def bev_map(self, batched_inputs, prepared=None):
+        """Voxelizer + sparse encoder: the dense BEV map the neck consumes (dynamic shapes end here)."""
+        samples = [bi[0] for bi in batched_inputs]
         batch_size = len(samples)
+        if prepared is not None:
+            assert prepared["batch_size"] == batch_size
+            self._adopt(prepared)
+            voxels, coords, npv, input_shape = (prepared[k] for k in ("voxels", "coords", "npv", "input_shape"))
+            return self.backbone(self.reader(voxels, npv), coords, batch_size, input_shape, indice_dict=prepared["indice_dict"])
         with torch.no_grad():
             if "voxels" in samples[0]:
                 voxels, coords, npv, input_shape = collate_voxels(samples, self.device)
             else:
                 voxels, coords, npv, input_shape = self.voxelize_on_device(samples)
-        x = self.reader(voxels, npv)
-        x = self.backbone(x, coords, batch_size, input_shape)
-        x = self.neck(x)
-        preds = self.center_head(x)
-        if self.training:
+        return self.backbone(self.reader(voxels, npv), coords, batch_size, input_shape)
+
+    def enable_static_graph(self, batched_inputs):
+        """Capture neck + heads + losses, forward and backward, into CUDA graphs (torch.cuda.make_graphed_callables): every
+        shape after the sparse encoder is fixed by the BEV grid, the batch size and max_objs.  Training mode, fixed batch
+        size, the job on a non-default stream.  Returns True on success; on failure the model keeps running eagerly and
+        the reason is kept in ``self.static_graph_error``."""
+        self.static_graph_error = None
+        try:
+            if not (self.training and self.device.type == "cuda"):
+                raise RuntimeError("needs a CUDA model in training mode")
+            bev = self.bev_map(batched_inputs)
             with torch.no_grad():
-                targets = self.label_assign(infos)
+                targets = self.label_assign([bi[1] for bi in batched_inputs])
+            section = _StaticSection(self)
+            flat = [t for k in self._TARGET_KEYS for t in targets[k]]
+            sample = (bev.detach().clone().requires_grad_(True),) + tuple(t.clone() for t in flat)
+            torch.cuda.synchronize()
+            self._static_call = torch.cuda.make_graphed_callables(section, sample, allow_unused_input=True)
+            self._static_section = [section]
+            self._static_batch = len(batched_inputs)
+            return True
+        except Exception as e:  # noqa: BLE001 — capture failures are reported, the eager path stays intact
+            self._static_call = None
+            self.static_graph_error = "%s: %s" % (type(e).__name__, e)
+            return False
+
+    def forward(self, batched_inputs, prepared=None):
+        """`prepared`: the result of prepare(batched_inputs) (optional; see there)."""
+        if self.training and self.device.type == "cuda":
+            ops.refresh_packs()   # every weight image the optimizer step made stale, in one launch
+        infos = [bi[1] for bi in batched_inputs]
+        x = self.bev_map(batched_inputs, prepared)
+        call = getattr(self, "_static_call", None)
+        if self.training:
+            if prepared is not None and prepared["targets"] is not None:
+                targets = prepared["targets"]
+            else:
+                with torch.no_grad():
+                    targets = self.label_assign(infos)
+            if call is not None and torch.is_grad_enabled() and len(batched_inputs) == self._static_batch:
+                section = self._static_section[0]
+                values = call(x, *[t for k in self._TARGET_KEYS for t in targets[k]])
+                return dict(zip(section.keys, values))
+        preds = self.center_head(self.neck(x))
+        if self.training:
             return self.center_head.loss(targets, preds)
         return self.center_head.decode(preds, self.config.model.post_process)
+
+
+class _StaticSection(nn.Module):
+    """Neck + heads + losses of CenterPoint as one callable over tensors (bev map, flattened targets) -> tuple of loss
+    terms: the part of a training step whose shapes never change.  Not registered as a sub-module of the detector."""
+
+    def __init__(self, det):
+        super().__init__()
+        self.det = [det]
+        self.neck = det.neck
+        self.center_head = det.center_head
+        self.keys = None
+
+    def forward(self, bev, *flat):
+        det = self.det[0]
+        tasks = len(det.tasks)
+        targets = {k: list(flat[i * tasks:(i + 1) * tasks]) for i, k in enumerate(det._TARGET_KEYS)}
+        out = det.center_head.loss(targets, det.center_head(det.neck(bev)))
+        if self.keys is None:
+            self.keys = sorted(out)
+        return tuple(out[k] for k in self.keys)
 
 
 def build_model(self, config, backend=None):

@@ -297,10 +297,28 @@ class SpMiddleResNetFHD(nn.Module):
         self.extra_conv = sp.SparseSequential(sp.SparseConv3d(128, 128, (3, 1, 1), (2, 1, 1), bias=False),
                                               get_norm(norm, 128), nn.ReLU())
 
-    def forward(self, voxel_features, coors, batch_size, input_shape):
+    def plan_geometry(self, coors, batch_size, input_shape):
+        """The strided rulebooks of the four downsampling convolutions for these voxel coordinates, without features
+        (see SparseResNet.plan_geometry): returns the indice_dict to hand to forward()."""
+        sp = self._sp[0]
+        plan = getattr(sp, "strided_rulebook", None)
+        if plan is None:
+            return None
+        sparse_shape = np.array(input_shape[::-1]) + [1, 0, 0]
+        cur = sp.SparseConvTensor(None, coors.int(), sparse_shape, batch_size)
+        indice_dict = cur.indice_dict
+        for seq in (self.conv2, self.conv3, self.conv4, self.extra_conv):
+            conv = seq[0]
+            rb = plan(cur, conv.kernel_size, conv.stride, conv.padding)
+            cur = sp.SparseConvTensor(None, rb.out_indices, rb.out_shape, batch_size, indice_dict=indice_dict)
+            cur._rows_sorted = True
+        return indice_dict
+
+    def forward(self, voxel_features, coors, batch_size, input_shape, indice_dict=None):
         sp = self._sp[0]
         sparse_shape = np.array(input_shape[::-1]) + [1, 0, 0]
-        x = sp.SparseConvTensor(voxel_features, coors.int(), sparse_shape, batch_size)
+        kw = {} if indice_dict is None else {"indice_dict": indice_dict}   # rulebooks planned ahead (plan_geometry)
+        x = sp.SparseConvTensor(voxel_features, coors.int(), sparse_shape, batch_size, **kw)
         x = self.conv_input(x)
         x_conv1 = self.conv1(x)
         x_conv2 = self.conv2(x_conv1)

@@ -53,3 +53,47 @@ def test_static_graph_equals_eager():
         rels = sorted(((ge[n] - gg[n]).norm() / ge[n].norm().clamp_min(1e-6)).item() for n in ge)
         # same kernels, same inputs: differences are atomics order only (see test_distributed_model.py for the noise floor)
         assert rels[len(rels) // 2] <= 0.05 and rels[int(len(rels) * 0.9)] <= 0.3, (rels[len(rels) // 2], rels[-1])
+
+
+def test_centerpoint_static_graph_and_prepared_step_match_eager():
+    """CenterPoint: neck + heads + losses in CUDA graphs, fed by prepare() from a side stream, give the eager losses and
+    gradients."""
+    from efg_b200.config import centerpoint_config
+    from efg_b200.detectors.centerpoint import VoxelNet
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_model_cpu import SMALL, small_batch
+
+    torch.manual_seed(0)
+    cfg = centerpoint_config(dataset={"pc_range": SMALL.pc_range, "voxel_size": SMALL.voxel_size, "max_voxel_num": 20000},
+                             model={"device": "cuda"})
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):   # captures need a non-default stream for the whole job
+        model = VoxelNet(cfg).train()
+        scenes = small_batch(2, 8000, seed=2)
+        inputs = [({"points": torch.from_numpy(p).cuda()}, {"annotations": a}) for p, a in scenes]
+
+        def run(prepared=None):
+            model.zero_grad(set_to_none=True)
+            losses = model(inputs) if prepared is None else model(inputs, prepared=prepared)
+            sum(v for k, v in losses.items() if k.endswith("_loss") and k.count("_") == 1).backward()
+            return {k: float(v) for k, v in losses.items()}, {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+
+        for m in model.modules():   # identical batch statistics on every call: freeze the running averages
+            if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+                m.momentum = 0.0
+        for _ in range(2):
+            eager_l, eager_g = run()
+        assert model.enable_static_graph(inputs), model.static_graph_error
+        prep = model.prepare(inputs, torch.cuda.Stream(priority=-1))
+        assert prep is not None and prep["targets"] is not None
+        graph_l, graph_g = run(prep)
+        torch.cuda.synchronize()
+    assert set(graph_l) == set(eager_l)
+    for k in eager_l:
+        assert abs(graph_l[k] - eager_l[k]) <= 1e-4 * max(1.0, abs(eager_l[k])), (k, graph_l[k], eager_l[k])
+    assert set(graph_g) == set(eager_g)
+    for n in eager_g:
+        scale = float(eager_g[n].abs().max())
+        if scale < 1e-3:
+            continue   # conv biases in front of a BatchNorm: the true gradient is zero, what is left is rounding noise
+        assert float((graph_g[n] - eager_g[n]).abs().max()) / scale < 2e-3, n
