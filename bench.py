@@ -426,18 +426,18 @@ def run_efgb200(args, backend=None):
     # CUDA graphs for the static-shape section of the step (FPN top-down, encoder, decoder, heads; forward + backward)
     graph_state = "none"
     if backend is None and not args.no_graph and not args.profile_step and hasattr(model, "enable_static_graph"):
-        if args.workload in ("voxel_detr", "centerpoint_waymo", "centerpoint_nusc"):
+        if True:
             ok = model.enable_static_graph([({"points": p}, {"annotations": a}) for p, a in resident[0]])
-            what = "static section (FPN top-down + transformer + heads), forward and backward" if args.workload == "voxel_detr" \
-                else "static section (RPN neck + centre heads + losses), forward and backward"
+            what = {"voxel_detr": "static section (FPN top-down + transformer + heads), forward and backward",
+                    "conquer": "encoder section (FPN top-down + encoder + proposal head), forward and backward; the decoders' "
+                               "length depends on the ground truth (denoising groups) and stays eager"}.get(
+                args.workload, "static section (RPN neck + centre heads + losses), forward and backward")
             graph_state = what if ok else "none (capture failed: %s)" % model.static_graph_error
             if not ok:
                 sys.stderr.write("bench.py: CUDA graph capture failed, running eagerly: %s\n" % model.static_graph_error)
             for i in range(3):
                 step(resident[i % n_batches])
             barrier()
-        else:
-            graph_state = "none (the denoising queries make the decoder length data-dependent)"
 
     if args.profile_step:
         ops.enable_nvtx()

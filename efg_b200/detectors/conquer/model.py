@@ -33,9 +33,14 @@ class ConQueRTransformer(Transformer):
         torch._foreach_mul_(k, self.m)
         torch._foreach_add_(k, q, alpha=1.0 - self.m)
 
-    def forward(self, src, pos, noised_gt_box=None, noised_gt_onehot=None, attn_mask=None, targets=None):
-        memory, anchors, shapes, start = self.encode(src, pos)
-        query_embed, query_pos, proposals, topk_indexes = self._get_enc_proposals(memory, anchors)
+    def forward(self, src, pos, noised_gt_box=None, noised_gt_onehot=None, attn_mask=None, targets=None, encoded=None):
+        """`encoded`: (memory, anchors, shapes, start, proposals, topk_indexes) of a graphed encoder section."""
+        if encoded is None:
+            memory, anchors, shapes, start = self.encode(src, pos)
+            query_embed, query_pos, proposals, topk_indexes = self._get_enc_proposals(memory, anchors)
+        else:
+            memory, anchors, shapes, start, proposals, topk_indexes = encoded
+            query_embed = query_pos = None
         noised = None
         if noised_gt_box is not None:
             noised = torch.cat((noised_gt_box, noised_gt_onehot), dim=-1)
@@ -69,6 +74,36 @@ class ConQueRTransformer(Transformer):
         return hs, init_ref, inter_refs, memory, anchors, topk_indexes
 
 
+class _EncoderSection(nn.Module):
+    """FPN top-down -> input projection -> position encoding -> box-attention encoder -> proposal head + top-k: the part
+    of a ConQueR step with fixed shapes (see ConQueR.enable_static_graph).  Not registered as a sub-module."""
+
+    def __init__(self, det, feat_names):
+        super().__init__()
+        ext = det.backbone.extractor
+        self.det = [det]
+        self.feat_names = list(feat_names)
+        self.lateral_convs = nn.ModuleList(ext.lateral_convs)
+        self.output_convs = nn.ModuleList(ext.output_convs)
+        self.input_proj = det.input_proj
+        self.encoder = det.transformer.encoder
+        self.proposal_head = det.transformer.proposal_head
+        self.meta = None
+
+    def forward(self, *maps):
+        det = self.det[0]
+        tr = det.transformer
+        feats = det.backbone.extractor.forward_dense(dict(zip(self.feat_names, maps)))
+        feats_pos = [(feats[f], det.backbone.position_encoding(feats[f]).type_as(feats[f])) for f in det.backbone.out_features]
+        features = [det.input_proj[i](fp[0]) for i, fp in enumerate(feats_pos)]
+        memory, anchors, shapes, start = tr.encode(features, [fp[1] for fp in feats_pos])
+        _, _, proposals, topk = tr._get_enc_proposals(memory, anchors)
+        enc_cls, enc_box = tr._enc_head_out
+        tr._enc_head_out = None
+        self.meta = (shapes, start)   # constants of the BEV geometry (Transformer._ref_cache)
+        return memory, anchors, proposals, topk, enc_cls, enc_box
+
+
 class ConQueR(VoxelDETR):
     def __init__(self, config, backend=None, prune_unused=True):
         super().__init__(config, backend=backend, prune_unused=prune_unused)
@@ -91,13 +126,49 @@ class ConQueR(VoxelDETR):
                                   backend=self.backend[0], num_classes=len(config.dataset.classes),
                                   mom=config.model.contrastive.mom)
 
-    def forward(self, batched_inputs):
+    def enable_static_graph(self, batched_inputs):
+        """ConQueR: the decoder input length depends on the ground truth of the batch (denoising groups), so only the
+        encoder section — FPN top-down, input projection, position encoding, box-attention encoder, proposal head and
+        top-k — is held in CUDA graphs, forward and backward; the decoders and the losses stay eager."""
+        self.static_graph_error = None
+        try:
+            if not (self.training and self.device.type == "cuda" and self.reuse_proposal_head):
+                raise RuntimeError("needs a CUDA model in training mode with reuse_proposal_head")
+            feats = self.bottom_up_maps(batched_inputs)
+            names = [n for n in self.backbone.extractor.in_features if n in feats]
+            section = _EncoderSection(self, names)
+            sample = tuple(feats[n].detach().clone().requires_grad_(True) for n in names)
+            torch.cuda.synchronize()
+            ops.PACKS_REFRESHED_PER_STEP = True   # see VoxelDETR.enable_static_graph
+            try:
+                self._static_call = torch.cuda.make_graphed_callables(section, sample, allow_unused_input=True)
+            finally:
+                ops.PACKS_REFRESHED_PER_STEP = False
+            self._static_packs = ops.pin_pack_cache()
+            self._static_names, self._static_batch = names, len(batched_inputs)
+            self._static_section = [section]
+            return True
+        except Exception as e:  # noqa: BLE001 — capture failures are reported, the eager path stays intact
+            self._static_call = None
+            self.static_graph_error = "%s: %s" % (type(e).__name__, e)
+            return False
+
+    def forward(self, batched_inputs, prepared=None):
         if self.training and self.device.type == "cuda":
             ops.refresh_packs()   # every weight image the optimizer step made stale, in one launch
         targets = self.encode_targets(batched_inputs) if self.training else None
         if targets is not None:
             self.transformer.proposal_head.losses.request_normaliser(targets, self.device)
-        features, pos = self.extract(batched_inputs)
+        call = getattr(self, "_static_call", None)
+        encoded = features = pos = None
+        if call is not None and self.training and torch.is_grad_enabled() and len(batched_inputs) == self._static_batch:
+            feats = self.bottom_up_maps(batched_inputs, prepared)
+            memory, anchors, proposals, topk, enc_cls, enc_box = call(*[feats[n] for n in self._static_names])
+            self.transformer._enc_head_out = (enc_cls, enc_box)
+            shapes, start = self._static_section[0].meta
+            encoded = (memory, anchors, shapes, start, proposals, topk)
+        else:
+            features, pos = self.extract(batched_inputs, prepared)
         dn = self.config.model.dn
         if self.training and dn.enabled and dn.dn_number > 0:
             q_label, q_box, attn_mask, dn_meta = prepare_for_cdn(targets, dn.dn_number, dn.dn_label_noise_ratio,
@@ -106,7 +177,7 @@ class ConQueR(VoxelDETR):
         else:
             q_label = q_box = attn_mask = dn_meta = None
         hs, init_ref, inter_refs, memory, anchors, topk_idx = self.transformer(features, pos, q_box, q_label, attn_mask,
-                                                                              targets=targets)
+                                                                              targets=targets, encoded=encoded)
         head = self.transformer.decoder.detection_head
         cls_out, box_out = [], []
         for i in range(hs.shape[0]):

@@ -97,3 +97,41 @@ def test_centerpoint_static_graph_and_prepared_step_match_eager():
         if scale < 1e-3:
             continue   # conv biases in front of a BatchNorm: the true gradient is zero, what is left is rounding noise
         assert float((graph_g[n] - eager_g[n]).abs().max()) / scale < 2e-3, n
+
+
+def test_conquer_encoder_graph_equals_eager():
+    """ConQueR: the encoder section replayed from CUDA graphs (decoders and losses eager) gives the eager losses and
+    gradients with identical denoising noise, on the captured batch and on another one."""
+    import model_cases as mc
+    from efg_b200.data import SceneSpec, make_scene
+    from efg_b200.detectors.conquer import ConQueR
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.cuda.stream(torch.cuda.Stream()):
+        cfg = mc.make_config("conquer", "cuda")
+        torch.manual_seed(0)
+        model = ConQueR(cfg).train()
+        model.load_state_dict(mc.fill_state_dict(model.state_dict()))
+        for m in model.modules():
+            if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+                m.momentum = 0.0
+        model.transformer.m = 1.0   # frozen momentum decoder: every run sees the same state
+        spec = SceneSpec(pc_range=mc.SMALL_RANGE, voxel_size=mc.VOXEL)
+        batches = [[make_scene(4000 + 500 * b, spec, seed=10 * b + i, num_objects=5 + b) for i in range(2)] for b in range(2)]
+
+        def run(b):
+            torch.manual_seed(7)   # the denoising noise is drawn from the global generator
+            return _step(model, b)
+
+        eager = [run(b) for b in batches]
+        assert model.enable_static_graph([({"points": torch.from_numpy(p).cuda()}, {"annotations": a}) for p, a in batches[0]]), \
+            model.static_graph_error
+        graphed = [run(b) for b in batches]
+    for (le, ge), (lg, gg) in zip(eager, graphed):
+        assert set(le) == set(lg)
+        for k in le:
+            assert abs(le[k] - lg[k]) <= 1e-4 * max(1.0, abs(le[k])), (k, le[k], lg[k])
+        assert set(ge) == set(gg)
+        rels = sorted(((ge[n] - gg[n]).norm() / ge[n].norm().clamp_min(1e-6)).item() for n in ge)
+        assert rels[len(rels) // 2] <= 0.05 and rels[int(len(rels) * 0.9)] <= 0.3, (rels[len(rels) // 2], rels[-1])
