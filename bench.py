@@ -324,8 +324,9 @@ def run_efgb200(args, backend=None):
     model.train()
     averager = GradAverager(model)
     averager.broadcast_parameters()
+    # the reference's optimizer (AdamW, VD/config.yaml solver); fused = torch's single multi-tensor CUDA implementation
     opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=0.01,
-                            betas=(0.9, 0.99), eps=1e-9)
+                            betas=(0.9, 0.99), eps=1e-9, fused=True)
 
     # a few distinct batches so consecutive steps do not see identical data
     n_batches = 2

@@ -401,11 +401,43 @@ def packed_weights(w_param, mode, split):
     return packed
 
 
+# Zero-padded copies of narrow weights ([c_out, taps, c_in < 16] -> 16 channels) for the tensor-core kernels; the copy is
+# refreshed when the parameter's version changes (refresh_packs() does it for all of them before it re-packs).
+PAD_NARROW_INPUTS = True
+_PADDED = {}   # key -> [version, padded weight, weakref(base parameter), weight view]
+
+
+def _refresh_padded(hit):
+    base = hit[2]()
+    if base is not None and hit[0] != base._version:
+        with torch.no_grad():
+            hit[1][..., :hit[3].shape[-1]].copy_(hit[3])
+        hit[0] = base._version
+
+
+def padded_weight(w_param, c_pad):
+    """w_param [c_out, taps, c_in] (a view of a Parameter) zero-padded to c_pad input channels, in a persistent buffer."""
+    base = w_param._base if w_param._base is not None else w_param
+    key = (w_param.data_ptr(), tuple(w_param.shape), c_pad, w_param.device.index)
+    hit = _PADDED.get(key)
+    if hit is None or hit[2]() is not base:
+        c_out, taps, _ = w_param.shape
+        buf = torch.zeros((c_out, taps, c_pad), dtype=w_param.dtype, device=w_param.device)
+        hit = _PADDED[key] = [-1, buf, weakref.ref(base), w_param.detach()]
+    _refresh_padded(hit)
+    return hit[1]
+
+
 def refresh_packs():
     """Re-pack, in one launch, every cached bf16x3 weight image whose parameter has been updated since it was packed
     (after optimizer.step: all of them).  Returns the number of images refreshed.  With PACKS_REFRESHED_PER_STEP set,
     CUDA-graph captures reuse the cached images instead of recording one pack kernel per layer — the caller then owes
     a refresh_packs() before every replay."""
+    for key, hit in list(_PADDED.items()):
+        if hit[2]() is None:
+            del _PADDED[key]
+        else:
+            _refresh_padded(hit)
     stale = []
     for key, hit in list(_PACK_CACHE.items()):
         base = hit[2]()

@@ -96,6 +96,14 @@ class _ToDenseFn(Function):
         return ops.dense_to_sparse(grad.contiguous(), indices), None, None, None
 
 
+def _padded_channels(c_in, c_out, taps):
+    """Narrow inputs (the 5 / 6 point features of the first convolution) do not fit the tensor-core kernels, whose
+    reduction runs in 16-byte pieces; zero-padded to 16 channels they do.  Returns 16 or None."""
+    if c_in >= 16 or ops.spconv_tc_supported(c_in, c_out, taps) or not ops.PAD_NARROW_INPUTS:
+        return None
+    return 16 if ops.spconv_tc_supported(16, c_out, taps) and ops.spconv_tc_wgrad_supported(16, c_out, taps) else None
+
+
 class _SparseConvFn(Function):
     """out = conv(features) over a rulebook; backward = dgrad (same kernel on the transposed
     rulebook) + wgrad.  ``weight`` is the parameter viewed as [Cout, taps, Cin]."""
@@ -105,13 +113,19 @@ class _SparseConvFn(Function):
         features = features.contiguous()
         weight = weight.contiguous()
         c_out, taps, c_in = weight.shape
-        if ops.spconv_tc_supported(c_in, c_out, taps):
+        pad_to = _padded_channels(c_in, c_out, taps) if features.is_cuda else None
+        if pad_to is not None:
+            # zero channels contribute nothing: same result from the tcgen05 kernels (forward here, wgrad in backward)
+            features = torch.nn.functional.pad(features, (0, pad_to - c_in))
+            out = ops.spconv_tc(features, ops.padded_weight(weight, pad_to), bias, rulebook.nbr, 0)
+        elif ops.spconv_tc_supported(c_in, c_out, taps):
             # `planes`: bf16 operand planes of `features` already produced by the fused BN + ReLU pass upstream
             out = ops.spconv_tc(features, weight, bias, rulebook.nbr, 0, planes=planes)
         else:
             out = ops.spconv_forward(features, weight.permute(1, 2, 0).contiguous(), bias, rulebook.nbr)
         ctx.rulebook = rulebook
         ctx.has_bias = bias is not None
+        ctx.pad_to = pad_to
         ctx.save_for_backward(features, weight)
         return out
 
@@ -134,7 +148,9 @@ class _SparseConvFn(Function):
                     w_t = w_t.flip(0)
                 d_feat = ops.spconv_forward(grad_out, w_t.contiguous(), None, table)
         if ctx.needs_input_grad[1]:
-            if ops.spconv_tc_wgrad_supported(c_in, c_out, taps):
+            if ctx.pad_to is not None:   # `features` are the padded rows saved by forward
+                d_w = ops.spconv_tc_wgrad(features, grad_out, rb.nbr, taps, ctx.pad_to, c_out)[..., :c_in].contiguous()
+            elif ops.spconv_tc_wgrad_supported(c_in, c_out, taps):
                 d_w = ops.spconv_tc_wgrad(features, grad_out, rb.nbr, taps, c_in, c_out)
             else:
                 d_w = ops.spconv_wgrad(features, grad_out, rb.nbr, taps, c_in, c_out).permute(2, 0, 1).contiguous()

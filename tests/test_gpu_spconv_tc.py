@@ -60,7 +60,7 @@ def test_tc_forward_vs_oracle(precision, mode, tol, cin, cout, m):
 
 
 @pytest.mark.parametrize("mode,tol", [("fp32x3", 2e-4), ("tf32", 1e-2), ("bf16x3", 5e-4)])
-@pytest.mark.parametrize("cin,cout", [(16, 16), (32, 64), (128, 128)])
+@pytest.mark.parametrize("cin,cout", [(16, 16), (32, 64), (128, 128), (5, 16), (6, 16)])   # 5 / 6: zero-padded to 16 channels
 @pytest.mark.parametrize("subm", [True, False])
 def test_tc_module_forward_backward_vs_oracle(precision, mode, tol, cin, cout, subm):
     from efg_b200.spconv import SparseConv3d, SparseConvTensor, SubMConv3d
