@@ -78,6 +78,11 @@ SIGNATURES = {
     "efgb_colsum_workspace_bytes": (_sz, [_i64, _int]),
     "efgb_colsum": (_int, [_vp, _i64, _int, _vp, _vp, _sz, _vp]),
     "efgb_box_attn_forward": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _int, _vp, _vp]),
+    "efgb_box_attn_fused_supported": (_int, [_int, _int, _int, _int]),
+    "efgb_box_attn_fused_forward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _i64, _i64, _int,
+                                           _vp, _vp]),
+    "efgb_box_attn_fused_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _i64, _i64,
+                                            _int, _vp, _vp, _vp, _vp]),
     "efgb_box_grid_softmax_forward": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _i64, _i64, _vp, _vp, _vp]),
     "efgb_box_grid_softmax_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _i64, _i64, _vp, _vp,
                                              _vp]),

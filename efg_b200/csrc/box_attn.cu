@@ -252,6 +252,85 @@ box_attn_bwd_kernel(const float* __restrict__ value, const int64_t* __restrict__
 // =================================================================================================
 constexpr int kTileWarps = 8;
 
+// ---- "where to attend" computed inside the attention kernels (fused variant, one level, <= 32 points) ----------------
+// Same arithmetic, in the same order, as box_grid_softmax_kernel below (Box3dAttention._where_to_attend + softmax,
+// VD/modules/box_attention.py:62-95,105-108): the sampling locations and attention weights never go through HBM —
+// the unfused pair writes and re-reads loc [B,LQ,H,P,2] + attn [B,LQ,H,P] (170 MB per encoder layer and direction).
+struct FusedArgs {
+  const float* offsets;   // [B*LQ rows, stride ld_offsets] : (h, nv) box offsets
+  const float* logits;    // [B*LQ rows, stride ld_logits]  : (h, p) attention logits
+  const float* ref;       // [B*LQ, 7]
+  const float* kidx;      // [P, 2]
+  int64_t ld_logits, ld_offsets;
+  int nv;                 // 4, or 5 with rotation
+  float* g_offsets;       // backward outputs, same strides
+  float* g_logits;
+};
+
+struct FusedPoint {
+  float a;                // softmax probability of this lane's point
+  float kx, ky;           // kernel offset of the point
+  float gx, gy;           // kidx * relu(size)
+  float cs, sn;
+  float w, l, sw, sl;     // reference size, box size before the relu
+};
+
+constexpr float kTwoPiF = 6.283185307179586f;
+
+__device__ __forceinline__ float2 fused_where(const FusedArgs& fa, int64_t bq, int h, int lane, int num_points, FusedPoint* fp) {
+  const float* r = fa.ref + bq * 7;
+  const float cx = __ldg(r + 0), cy = __ldg(r + 1), w = __ldg(r + 3), l = __ldg(r + 4), ref_angle = __ldg(r + 6);
+  const float* lg = fa.logits + bq * fa.ld_logits + static_cast<int64_t>(h) * num_points;
+  const float x = lane < num_points ? __ldg(lg + lane) : -INFINITY;
+  float m = x;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+  const float e = lane < num_points ? expf(x - m) : 0.f;
+  const float inv = 1.f / warp_sum(e);
+  fp->a = e * inv;
+  const float* off = fa.offsets + bq * fa.ld_offsets + static_cast<int64_t>(h) * fa.nv;
+  const float o0 = __ldg(off + 0), o1 = __ldg(off + 1), o2 = __ldg(off + 2), o3 = __ldg(off + 3);
+  const float bx = cx + o0 / 8.f * w, by = cy + o1 / 8.f * l;
+  fp->w = w;
+  fp->l = l;
+  fp->sw = w + o2 / 8.f * w;
+  fp->sl = l + o3 / 8.f * l;
+  const float angle = fa.nv == 5 ? (ref_angle + __ldg(off + 4) / 16.f) * kTwoPiF : ref_angle;
+  sincosf(angle, &fp->sn, &fp->cs);
+  const float rw = fmaxf(fp->sw, 0.f), rl = fmaxf(fp->sl, 0.f);
+  fp->kx = fp->ky = 0.f;
+  if (lane < num_points) {
+    fp->kx = __ldg(fa.kidx + 2 * lane);
+    fp->ky = __ldg(fa.kidx + 2 * lane + 1);
+  }
+  fp->gx = fp->kx * rw;
+  fp->gy = fp->ky * rl;
+  return make_float2(bx + (fp->gx * fp->cs - fp->gy * fp->sn), by + (fp->gx * fp->sn + fp->gy * fp->cs));
+}
+
+// Backward of fused_where for one (b, q, h): (g_xy, g_a) of the lane's point -> gradients of the logits and offsets rows.
+__device__ __forceinline__ void fused_where_backward(const FusedArgs& fa, int64_t bq, int h, int lane, int num_points,
+                                                     const FusedPoint& fp, float gxy_x, float gxy_y, float ga) {
+  const float dot = warp_sum(fp.a * ga);
+  if (lane < num_points)
+    fa.g_logits[bq * fa.ld_logits + static_cast<int64_t>(h) * num_points + lane] = fp.a * (ga - dot);
+  const float ggx = gxy_x * fp.cs + gxy_y * fp.sn;    // d loss / d gx
+  const float ggy = -gxy_x * fp.sn + gxy_y * fp.cs;   // d loss / d gy
+  const float a_cx = warp_sum(gxy_x);
+  const float a_cy = warp_sum(gxy_y);
+  const float a_sw = warp_sum(ggx * fp.kx);
+  const float a_sl = warp_sum(ggy * fp.ky);
+  const float a_ang = warp_sum(gxy_x * (-fp.gx * fp.sn - fp.gy * fp.cs) + gxy_y * (fp.gx * fp.cs - fp.gy * fp.sn));
+  if (lane == 0) {
+    float* go = fa.g_offsets + bq * fa.ld_offsets + static_cast<int64_t>(h) * fa.nv;
+    go[0] = a_cx * fp.w / 8.f;
+    go[1] = a_cy * fp.l / 8.f;
+    go[2] = (fp.sw > 0.f ? a_sw : 0.f) * fp.w / 8.f;
+    go[3] = (fp.sl > 0.f ? a_sl : 0.f) * fp.l / 8.f;
+    if (fa.nv == 5) go[4] = a_ang * kTwoPiF / 16.f;
+  }
+}
+
 struct TileGeom {
   int qw, qh;   // query grid (qw = 8, qh = ceil(LQ / 8) when no grid hint was given)
   int tx, ty;   // tiles along x / y
@@ -280,11 +359,12 @@ __device__ __forceinline__ void tile_fill_taps(int2* my, const int lane, const b
   }
 }
 
+template <bool kFused>
 __global__ void __launch_bounds__(kTileWarps * 32)
 box_attn_fwd_tile_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
                          const int64_t* __restrict__ level_start, const float* __restrict__ loc,
-                         const float* __restrict__ attn, const TileGeom g, int len_value, int num_heads, int num_levels,
-                         int len_query, int num_points, float* __restrict__ out) {
+                         const float* __restrict__ attn, const FusedArgs fa, const TileGeom g, int len_value, int num_heads,
+                         int num_levels, int len_query, int num_points, float* __restrict__ out) {
   __shared__ int2 taps[kTileWarps][32 * 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cg = lane >> 3;        // corner group
@@ -317,7 +397,11 @@ box_attn_fwd_tile_kernel(const float* __restrict__ value, const int64_t* __restr
         const int np = min(32, num_points - p0);
         float2 xy = make_float2(0.f, 0.f);
         float a = 0.f;
-        if (p < num_points) {
+        if constexpr (kFused) {   // one level, num_points <= 32: this loop body runs once per (q, h)
+          FusedPoint fp;
+          xy = fused_where(fa, b * len_query + q, h, lane, num_points, &fp);
+          a = fp.a;
+        } else if (p < num_points) {
           xy = __ldg(reinterpret_cast<const float2*>(loc_q + (l * num_points + p) * 2));
           a = __ldg(attn_q + l * num_points + p);
         }
@@ -361,11 +445,12 @@ box_attn_fwd_tile_kernel(const float* __restrict__ value, const int64_t* __restr
   }
 }
 
+template <bool kFused>
 __global__ void __launch_bounds__(kTileWarps * 32)
 box_attn_bwd_tile_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
                          const int64_t* __restrict__ level_start, const float* __restrict__ loc,
-                         const float* __restrict__ attn, const float* __restrict__ grad_out, const TileGeom g,
-                         int len_value, int num_heads, int num_levels, int len_query, int num_points,
+                         const float* __restrict__ attn, const float* __restrict__ grad_out, const FusedArgs fa,
+                         const TileGeom g, int len_value, int num_heads, int num_levels, int len_query, int num_points,
                          float* __restrict__ grad_value, float* __restrict__ grad_loc, float* __restrict__ grad_attn) {
   __shared__ int2 taps[kTileWarps][32 * 4];
   __shared__ __align__(16) float dots[kTileWarps][32 * 4];  // [tap][corner] = <value_corner, grad_out>
@@ -405,7 +490,11 @@ box_attn_bwd_tile_kernel(const float* __restrict__ value, const int64_t* __restr
         const int np = min(32, num_points - p0);
         float2 xy = make_float2(0.f, 0.f);
         float a = 0.f;
-        if (p < num_points) {
+        [[maybe_unused]] FusedPoint fp;
+        if constexpr (kFused) {
+          xy = fused_where(fa, b * len_query + q, h, lane, num_points, &fp);
+          a = fp.a;
+        } else if (p < num_points) {
           xy = __ldg(reinterpret_cast<const float2*>(loc_q + (l * num_points + p) * 2));
           a = __ldg(attn_q + l * num_points + p);
         }
@@ -459,9 +548,9 @@ box_attn_bwd_tile_kernel(const float* __restrict__ value, const int64_t* __restr
           mydots[(t0 + (lane & 7)) * 4 + cg] = tot;
         }
         __syncwarp();
-        if (p < num_points) {
+        {
           float gx = 0.f, gy = 0.f, ga = 0.f;
-          if (made) {
+          if (p < num_points && made) {
             const float4 D = *reinterpret_cast<const float4*>(mydots + lane * 4);
             ga = c.w1 * D.x + c.w2 * D.y + c.w3 * D.z + c.w4 * D.w;
             const float gw = c.hh * (D.y - D.x) + c.lh * (D.w - D.z);
@@ -469,8 +558,12 @@ box_attn_bwd_tile_kernel(const float* __restrict__ value, const int64_t* __restr
             gx = static_cast<float>(Wl) * gw * a;
             gy = static_cast<float>(Hl) * gh * a;
           }
-          *reinterpret_cast<float2*>(grad_loc + (idx * lp + l * num_points + p) * 2) = make_float2(gx, gy);
-          grad_attn[idx * lp + l * num_points + p] = ga;
+          if constexpr (kFused) {
+            fused_where_backward(fa, b * len_query + q, h, lane, num_points, fp, gx, gy, ga);
+          } else if (p < num_points) {
+            *reinterpret_cast<float2*>(grad_loc + (idx * lp + l * num_points + p) * 2) = make_float2(gx, gy);
+            grad_attn[idx * lp + l * num_points + p] = ga;
+          }
         }
       }
     }
@@ -528,8 +621,9 @@ extern "C" int efgb_box_attn_forward(const float* value, const int64_t* spatial_
     const TileGeom g = tile_geom(len_query, query_grid_w, nw);
     const int64_t blocks = static_cast<int64_t>(batch) * num_heads * g.tx * g.ty;
     EFGB_REQUIRE(blocks < (1ll << 31), EFGB_EINVAL, "box_attn_forward: too many query tiles");
-    box_attn_fwd_tile_kernel<<<static_cast<unsigned>(blocks), kTileWarps * 32, 0, stream>>>(
-        value, spatial_shapes, level_start, loc, attn, g, len_value, num_heads, num_levels, len_query, num_points, out);
+    box_attn_fwd_tile_kernel<false><<<static_cast<unsigned>(blocks), kTileWarps * 32, 0, stream>>>(
+        value, spatial_shapes, level_start, loc, attn, FusedArgs{}, g, len_value, num_heads, num_levels, len_query, num_points,
+        out);
     EFGB_LAUNCH_OK("box_attn_fwd_tile_kernel");
     return EFGB_OK;
   }
@@ -567,8 +661,8 @@ extern "C" int efgb_box_attn_backward(const float* value, const int64_t* spatial
     const TileGeom g = tile_geom(len_query, query_grid_w, nw);
     const int64_t blocks = static_cast<int64_t>(batch) * num_heads * g.tx * g.ty;
     EFGB_REQUIRE(blocks < (1ll << 31), EFGB_EINVAL, "box_attn_backward: too many query tiles");
-    box_attn_bwd_tile_kernel<<<static_cast<unsigned>(blocks), kTileWarps * 32, 0, stream>>>(
-        value, spatial_shapes, level_start, loc, attn, grad_out, g, len_value, num_heads, num_levels, len_query,
+    box_attn_bwd_tile_kernel<false><<<static_cast<unsigned>(blocks), kTileWarps * 32, 0, stream>>>(
+        value, spatial_shapes, level_start, loc, attn, grad_out, FusedArgs{}, g, len_value, num_heads, num_levels, len_query,
         num_points, grad_value, grad_loc, grad_attn);
     EFGB_LAUNCH_OK("box_attn_bwd_tile_kernel");
     return EFGB_OK;
@@ -584,6 +678,85 @@ extern "C" int efgb_box_attn_backward(const float* value, const int64_t* spatial
   else EFGB_BWD(4);
 #undef EFGB_BWD
   EFGB_LAUNCH_OK("box_attn_bwd_kernel");
+  return EFGB_OK;
+}
+
+// Fused variant: sampling grid + softmax computed inside the tile kernels (one level, head_dim 32, <= 32 points).
+extern "C" int efgb_box_attn_fused_supported(int head_dim, int num_levels, int num_points, int num_variables) {
+  return (head_dim == 32 && num_levels == 1 && num_points >= 1 && num_points <= 32 && (num_variables == 4 || num_variables == 5)) ? 1 : 0;
+}
+
+extern "C" int efgb_box_attn_fused_forward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start,
+                                           const float* offsets, const float* logits, const float* ref_windows,
+                                           const float* kernel_indices, int batch, int len_value, int num_heads, int len_query,
+                                           int num_points, int num_variables, int64_t logits_row_stride,
+                                           int64_t offsets_row_stride, int query_grid_w, float* out, efgb_stream_t stream_) {
+  cudaStream_t stream = as_stream(stream_);
+  int rc = check_args(batch, len_value, num_heads, 32, 1, len_query, num_points, "box_attn_fused_forward");
+  if (rc != EFGB_OK) return rc;
+  EFGB_REQUIRE(efgb_box_attn_fused_supported(32, 1, num_points, num_variables) &&
+                   static_cast<int64_t>(len_value) * num_heads * 32 < (1ll << 31),
+               EFGB_EINVAL, "box_attn_fused_forward: unsupported shape");
+  const int64_t nw = static_cast<int64_t>(batch) * len_query * num_heads;
+  if (nw == 0) return EFGB_OK;
+  EFGB_REQUIRE(value && spatial_shapes && level_start && offsets && logits && ref_windows && kernel_indices && out, EFGB_EINVAL,
+               "box_attn_fused_forward: null pointer");
+  FusedArgs fa{};
+  fa.offsets = offsets;
+  fa.logits = logits;
+  fa.ref = ref_windows;
+  fa.kidx = kernel_indices;
+  fa.ld_logits = logits_row_stride > 0 ? logits_row_stride : static_cast<int64_t>(num_heads) * num_points;
+  fa.ld_offsets = offsets_row_stride > 0 ? offsets_row_stride : static_cast<int64_t>(num_heads) * num_variables;
+  fa.nv = num_variables;
+  const TileGeom g = tile_geom(len_query, query_grid_w, nw);
+  const int64_t blocks = static_cast<int64_t>(batch) * num_heads * g.tx * g.ty;
+  EFGB_REQUIRE(blocks < (1ll << 31), EFGB_EINVAL, "box_attn_fused_forward: too many query tiles");
+  box_attn_fwd_tile_kernel<true><<<static_cast<unsigned>(blocks), kTileWarps * 32, 0, stream>>>(
+      value, spatial_shapes, level_start, nullptr, nullptr, fa, g, len_value, num_heads, 1, len_query, num_points, out);
+  EFGB_LAUNCH_OK("box_attn_fwd_tile_kernel<fused>");
+  return EFGB_OK;
+}
+
+extern "C" int efgb_box_attn_fused_backward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start,
+                                            const float* offsets, const float* logits, const float* ref_windows,
+                                            const float* kernel_indices, const float* grad_out, int batch, int len_value,
+                                            int num_heads, int len_query, int num_points, int num_variables,
+                                            int64_t logits_row_stride, int64_t offsets_row_stride, int query_grid_w,
+                                            float* grad_value, float* grad_offsets, float* grad_logits, efgb_stream_t stream_) {
+  cudaStream_t stream = as_stream(stream_);
+  int rc = check_args(batch, len_value, num_heads, 32, 1, len_query, num_points, "box_attn_fused_backward");
+  if (rc != EFGB_OK) return rc;
+  EFGB_REQUIRE(efgb_box_attn_fused_supported(32, 1, num_points, num_variables) &&
+                   static_cast<int64_t>(len_value) * num_heads * 32 < (1ll << 31),
+               EFGB_EINVAL, "box_attn_fused_backward: unsupported shape");
+  const size_t vbytes = static_cast<size_t>(batch) * len_value * num_heads * 32 * sizeof(float);
+  if (vbytes) {
+    EFGB_REQUIRE(grad_value, EFGB_EINVAL, "box_attn_fused_backward: null grad_value");
+    EFGB_CUDA_OK(cudaMemsetAsync(grad_value, 0, vbytes, stream));
+  }
+  const int64_t nw = static_cast<int64_t>(batch) * len_query * num_heads;
+  if (nw == 0) return EFGB_OK;
+  EFGB_REQUIRE(value && spatial_shapes && level_start && offsets && logits && ref_windows && kernel_indices && grad_out &&
+                   grad_offsets && grad_logits,
+               EFGB_EINVAL, "box_attn_fused_backward: null pointer");
+  FusedArgs fa{};
+  fa.offsets = offsets;
+  fa.logits = logits;
+  fa.ref = ref_windows;
+  fa.kidx = kernel_indices;
+  fa.ld_logits = logits_row_stride > 0 ? logits_row_stride : static_cast<int64_t>(num_heads) * num_points;
+  fa.ld_offsets = offsets_row_stride > 0 ? offsets_row_stride : static_cast<int64_t>(num_heads) * num_variables;
+  fa.nv = num_variables;
+  fa.g_offsets = grad_offsets;
+  fa.g_logits = grad_logits;
+  const TileGeom g = tile_geom(len_query, query_grid_w, nw);
+  const int64_t blocks = static_cast<int64_t>(batch) * num_heads * g.tx * g.ty;
+  EFGB_REQUIRE(blocks < (1ll << 31), EFGB_EINVAL, "box_attn_fused_backward: too many query tiles");
+  box_attn_bwd_tile_kernel<true><<<static_cast<unsigned>(blocks), kTileWarps * 32, 0, stream>>>(
+      value, spatial_shapes, level_start, nullptr, nullptr, grad_out, fa, g, len_value, num_heads, 1, len_query, num_points,
+      grad_value, nullptr, nullptr);
+  EFGB_LAUNCH_OK("box_attn_bwd_tile_kernel<fused>");
   return EFGB_OK;
 }
 

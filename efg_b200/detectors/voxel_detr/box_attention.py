@@ -105,6 +105,13 @@ class Box3dAttention(nn.Module):
                     ws.append(self.linear_attn_weight.new_zeros((pad, self.d_model)))
                     bs.append(self.linear_attn_bias.new_zeros((pad,)))
                 proj = ops.dense_linear(query, torch.cat(ws, 0), torch.cat(bs, 0))
+                if ops.box_attn_fused_supported(self.head_dim, self.num_level, self.num_point, self.num_variable):
+                    # sampling grid + softmax inside the attention kernels: `grid` / `attn` never exist in memory (the
+                    # attention weights, which no caller of this module uses, are not returned on this path)
+                    out = ops.BoxAttnProjFunction.apply(value, v_shape, v_start_index, proj, ref_windows, self.kernel_indices,
+                                                        self.num_head, self.num_variable,
+                                                        ops._query_grid_width(v_shape, self.num_level, LQ))
+                    return self.out_proj(out), None
                 grid, attn = ops.BoxProjGridSoftmaxFunction.apply(proj, ref_windows, self.kernel_indices, self.num_head,
                                                                   self.num_level, self.num_variable)
             else:

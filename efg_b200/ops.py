@@ -952,6 +952,71 @@ class BoxProjGridSoftmaxFunction(torch.autograd.Function):
         return g_proj, None, None, None, None, None
 
 
+FUSE_BOX_ATTENTION = True   # Box3dAttention: sampling grid + softmax inside the attention kernels when the shape allows
+
+
+def box_attn_fused_supported(head_dim, num_levels, num_points, num_variables):
+    return FUSE_BOX_ATTENTION and bool(_lib.lib().efgb_box_attn_fused_supported(head_dim, num_levels, num_points, num_variables))
+
+
+class BoxAttnProjFunction(torch.autograd.Function):
+    """Box3dAttention from the projection output to the attended values as ONE operator per direction:
+    out = box_attn(value, where_to_attend(proj offsets, ref_windows), softmax(proj logits)) with the sampling locations and
+    attention weights computed inside the attention kernels (csrc/box_attn.cu, fused tile kernels).
+    proj [B, LQ, ld] = [attention logits (H*P) | box offsets (H*NV) | padding], value [B, LV, H, 32], one value level."""
+
+    @staticmethod
+    def forward(ctx, value, shapes, level_start, proj, ref_windows, kernel_indices, num_heads, num_variables, query_grid_w):
+        value, proj = value.contiguous(), proj.contiguous()
+        ref_windows, kernel_indices = ref_windows.contiguous(), kernel_indices.contiguous()
+        for t, n in ((value, "value"), (proj, "proj"), (ref_windows, "ref_windows"), (kernel_indices, "kernel_indices")):
+            _check(t, n, torch.float32)
+        _check(shapes, "value_spatial_shapes", torch.int64)
+        _check(level_start, "value_level_start_index", torch.int64)
+        b, lv, h, ch = value.shape
+        _, lq, ld = proj.shape
+        npnt = kernel_indices.shape[0]
+        n_attn, n_box = num_heads * npnt, num_heads * num_variables
+        if h != num_heads or ch != 32 or shapes.shape[0] != 1 or ld < n_attn + n_box or ref_windows.shape != (b, lq, 7):
+            raise RuntimeError("box_attn_proj: inconsistent shapes %r %r %r" % (tuple(value.shape), tuple(proj.shape), tuple(ref_windows.shape)))
+        out = torch.empty((b, lq, h * ch), dtype=torch.float32, device=value.device)
+        off_ptr = ctypes.c_void_p(proj.data_ptr() + 4 * n_attn)
+        t0 = PROFILER.begin() if PROFILER is not None else None
+        _lib.check(_lib.lib().efgb_box_attn_fused_forward(_p(value), _p(shapes), _p(level_start), off_ptr, _p(proj), _p(ref_windows),
+                                                          _p(kernel_indices), b, lv, h, lq, npnt, num_variables, ld, ld,
+                                                          int(query_grid_w), _p(out), _stream()), "box_attn_fused_forward")
+        if t0 is not None:
+            PROFILER.end("box_attn_fwd", t0, 4 * (value.numel() + b * lq * (n_attn + n_box) + out.numel()), 2 * 4 * b * lq * h * npnt * ch)
+        ctx.save_for_backward(value, shapes, level_start, proj, ref_windows, kernel_indices)
+        ctx.dims = (num_heads, num_variables, n_attn, n_box, int(query_grid_w))
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        value, shapes, level_start, proj, ref_windows, kernel_indices = ctx.saved_tensors
+        num_heads, num_variables, n_attn, n_box, qgw = ctx.dims
+        grad_out = grad_out.contiguous()
+        b, lv, h, ch = value.shape
+        _, lq, ld = proj.shape
+        npnt = kernel_indices.shape[0]
+        g_value = torch.empty_like(value)
+        g_proj = torch.empty_like(proj)
+        if ld > n_attn + n_box:
+            g_proj[..., n_attn + n_box:].zero_()
+        off_ptr = ctypes.c_void_p(proj.data_ptr() + 4 * n_attn)
+        g_off_ptr = ctypes.c_void_p(g_proj.data_ptr() + 4 * n_attn)
+        t0 = PROFILER.begin() if PROFILER is not None else None
+        _lib.check(_lib.lib().efgb_box_attn_fused_backward(_p(value), _p(shapes), _p(level_start), off_ptr, _p(proj), _p(ref_windows),
+                                                           _p(kernel_indices), _p(grad_out), b, lv, h, lq, npnt, num_variables, ld,
+                                                           ld, qgw, _p(g_value), g_off_ptr, _p(g_proj), _stream()),
+                   "box_attn_fused_backward")
+        if t0 is not None:
+            PROFILER.end("box_attn_bwd", t0, 4 * (2 * value.numel() + 2 * b * lq * (n_attn + n_box) + grad_out.numel()),
+                         3 * 2 * 4 * b * lq * h * npnt * ch)
+        return g_value, None, None, g_proj, None, None, None, None, None
+
+
 # --------------------------------------------------------------------------------------------
 # fused BatchNorm1d (+ residual) (+ ReLU) on the rows of a sparse tensor
 # --------------------------------------------------------------------------------------------

@@ -372,6 +372,23 @@ int efgb_box_grid_softmax_backward(const float* offsets, const float* logits, co
                                    int64_t offsets_row_stride, float* grad_offsets, float* grad_logits,
                                    efgb_stream_t stream);
 
+/* Box attention with the sampling grid and the softmax computed INSIDE the attention kernels: Box3dAttention.forward
+ * (VD/modules/box_attention.py:97-115: _where_to_attend -> softmax -> BoxAttnFunction) as one operator over the outputs
+ * of its two linear layers; `loc` / `attn` never exist in memory.  One value level, head_dim 32, <= 32 sampling points
+ * (efgb_box_attn_fused_supported); arguments as efgb_box_grid_softmax_* and efgb_box_attn_*; grad_value is zeroed inside. */
+int efgb_box_attn_fused_supported(int head_dim, int num_levels, int num_points, int num_variables);
+int efgb_box_attn_fused_forward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start,
+                                const float* offsets, const float* logits, const float* ref_windows,
+                                const float* kernel_indices, int batch, int len_value, int num_heads, int len_query,
+                                int num_points, int num_variables, int64_t logits_row_stride, int64_t offsets_row_stride,
+                                int query_grid_w, float* out, efgb_stream_t stream);
+int efgb_box_attn_fused_backward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start,
+                                 const float* offsets, const float* logits, const float* ref_windows,
+                                 const float* kernel_indices, const float* grad_out, int batch, int len_value,
+                                 int num_heads, int len_query, int num_points, int num_variables,
+                                 int64_t logits_row_stride, int64_t offsets_row_stride, int query_grid_w,
+                                 float* grad_value, float* grad_offsets, float* grad_logits, efgb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -174,6 +174,7 @@ def test_refresh_packs_repacks_every_stale_image_in_one_launch(precision):
     cached bf16x3 weight image to what the per-layer pack produces, for forward and both dgrad layouts."""
     ops = precision
     ops.CONV_PRECISION = "bf16x3"
+    ops._PACK_PINNED.clear()   # graphs captured by earlier tests of this process are gone
     ops.clear_pack_cache()
     torch.manual_seed(5)
     shapes = [(16, 27, 16), (64, 27, 32), (128, 27, 128), (256, 1, 256), (1024, 1, 256), (32, 8, 16)]
