@@ -114,6 +114,10 @@ class ClockSampler:
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
         except Exception:
             self.nvml = None
+        # The first clock / reason query of a process takes ~60 ms on a fresh box and holds a driver lock the launching
+        # thread needs: take it (and throw it away) here, outside the timed region.
+        self.sample()
+        self.sm, self.reasons, self.cost_ms = [], set(), []
 
     def sample(self):
         t0 = time.perf_counter()

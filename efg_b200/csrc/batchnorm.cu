@@ -87,34 +87,39 @@ stats_partial_kernel(const float* __restrict__ x, const float* __restrict__ dy, 
   }
 }
 
-// The per-slab partial sums are folded by 32 columns x 8 slab lanes per CTA with independent loads (a single thread
-// walking ~600 slabs is a chain of dependent L2 reads: measured 60 us, the whole normalisation pass took less).
+// The per-slab partial sums are folded by kFoldCols columns x kFoldLanes slab lanes per CTA with independent loads (a single
+// thread walking ~600 slabs is a chain of dependent L2 reads: measured 60 us, the whole normalisation pass took less;
+// 32 columns x 8 lanes still took 18 us per BatchNorm — 74 slabs per thread — against ~6 us for the other two kernels).
+constexpr int kFoldCols = 8;
+constexpr int kFoldLanes = 32;
+static_assert(kFoldCols * kFoldLanes == 256, "the final kernels run 256 threads");
+
 __device__ __forceinline__ void fold_partials(const float* __restrict__ partial, int slabs, int cols, int c, int ty, double& s1,
-                                              double& s2, double (*red)[2][33]) {
+                                              double& s2, double (*red)[2][kFoldCols + 1]) {
   s1 = 0.0;
   s2 = 0.0;
   if (c < cols) {
     int k = ty;
-    for (; k + 24 < slabs; k += 32) {   // four independent pairs of loads in flight
+    for (; k + 3 * kFoldLanes < slabs; k += 4 * kFoldLanes) {   // four independent pairs of loads in flight
       const float a0 = partial[static_cast<int64_t>(k) * 2 * cols + c], b0 = partial[static_cast<int64_t>(k) * 2 * cols + cols + c];
-      const float a1 = partial[static_cast<int64_t>(k + 8) * 2 * cols + c], b1 = partial[static_cast<int64_t>(k + 8) * 2 * cols + cols + c];
-      const float a2 = partial[static_cast<int64_t>(k + 16) * 2 * cols + c], b2 = partial[static_cast<int64_t>(k + 16) * 2 * cols + cols + c];
-      const float a3 = partial[static_cast<int64_t>(k + 24) * 2 * cols + c], b3 = partial[static_cast<int64_t>(k + 24) * 2 * cols + cols + c];
+      const float a1 = partial[static_cast<int64_t>(k + kFoldLanes) * 2 * cols + c], b1 = partial[static_cast<int64_t>(k + kFoldLanes) * 2 * cols + cols + c];
+      const float a2 = partial[static_cast<int64_t>(k + 2 * kFoldLanes) * 2 * cols + c], b2 = partial[static_cast<int64_t>(k + 2 * kFoldLanes) * 2 * cols + cols + c];
+      const float a3 = partial[static_cast<int64_t>(k + 3 * kFoldLanes) * 2 * cols + c], b3 = partial[static_cast<int64_t>(k + 3 * kFoldLanes) * 2 * cols + cols + c];
       s1 += (static_cast<double>(a0) + a1) + (static_cast<double>(a2) + a3);
       s2 += (static_cast<double>(b0) + b1) + (static_cast<double>(b2) + b3);
     }
-    for (; k < slabs; k += 8) {
+    for (; k < slabs; k += kFoldLanes) {
       s1 += static_cast<double>(partial[static_cast<int64_t>(k) * 2 * cols + c]);
       s2 += static_cast<double>(partial[static_cast<int64_t>(k) * 2 * cols + cols + c]);
     }
   }
-  const int tx = threadIdx.x & 31;
+  const int tx = threadIdx.x % kFoldCols;
   red[ty][0][tx] = s1;
   red[ty][1][tx] = s2;
   __syncthreads();
   if (ty == 0) {
 #pragma unroll
-    for (int j = 1; j < 8; ++j) {
+    for (int j = 1; j < kFoldLanes; ++j) {
       s1 += red[j][0][tx];
       s2 += red[j][1][tx];
     }
@@ -125,8 +130,8 @@ __global__ void __launch_bounds__(256)
 stats_final_fwd_kernel(const float* __restrict__ partial, int slabs, int cols, int64_t rows, float eps, float momentum,
                        float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ mean,
                        float* __restrict__ rstd) {
-  __shared__ double red[8][2][33];
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31), ty = threadIdx.x >> 5;
+  __shared__ double red[kFoldLanes][2][kFoldCols + 1];
+  const int c = blockIdx.x * kFoldCols + (threadIdx.x % kFoldCols), ty = threadIdx.x / kFoldCols;
   double s1, s2;
   fold_partials(partial, slabs, cols, c, ty, s1, s2, red);
   if (ty != 0 || c >= cols) return;
@@ -153,8 +158,8 @@ stats_eval_kernel(const float* __restrict__ running_mean, const float* __restric
 
 __global__ void __launch_bounds__(256)
 stats_final_bwd_kernel(const float* __restrict__ partial, int slabs, int cols, float* __restrict__ dbeta, float* __restrict__ dgamma) {
-  __shared__ double red[8][2][33];
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31), ty = threadIdx.x >> 5;
+  __shared__ double red[kFoldLanes][2][kFoldCols + 1];
+  const int c = blockIdx.x * kFoldCols + (threadIdx.x % kFoldCols), ty = threadIdx.x / kFoldCols;
   double s1, s2;
   fold_partials(partial, slabs, cols, c, ty, s1, s2, red);
   if (ty != 0 || c >= cols) return;
@@ -236,7 +241,7 @@ static bool supported(int cols) { return cols >= 4 && cols % 4 == 0 && cols / 4 
 
 static int num_slabs(int64_t rows, int cols) {
   const int lanes = kThreads / (cols / 4) > 0 ? kThreads / (cols / 4) : 1;
-  int64_t slabs = static_cast<int64_t>(kNumSMs) * 4;
+  int64_t slabs = static_cast<int64_t>(kNumSMs) * 2;
   const int64_t max_slabs = (rows + 4 * lanes - 1) / (4 * lanes);
   if (slabs > max_slabs) slabs = max_slabs;
   if (slabs < 1) slabs = 1;
@@ -275,7 +280,7 @@ extern "C" int efgb_bn_forward(const float* x, int64_t rows, int cols, const flo
     bn::stats_partial_kernel<false><<<slabs, bn::kThreads, 0, stream>>>(x, nullptr, nullptr, nullptr, nullptr, rows, cols, 0,
                                                                      rows_per_slab, partial);
     EFGB_LAUNCH_OK("bn::stats_partial_kernel");
-    bn::stats_final_fwd_kernel<<<(cols + 31) / 32, 256, 0, stream>>>(partial, slabs, cols, rows, eps, momentum, running_mean,
+    bn::stats_final_fwd_kernel<<<(cols + bn::kFoldCols - 1) / bn::kFoldCols, 256, 0, stream>>>(partial, slabs, cols, rows, eps, momentum, running_mean,
                                                                       running_var, save_mean, save_rstd);
     EFGB_LAUNCH_OK("bn::stats_final_fwd_kernel");
   } else {
@@ -307,7 +312,7 @@ extern "C" int efgb_bn_backward(const float* dy, const float* x, const float* y,
   bn::stats_partial_kernel<true><<<slabs, bn::kThreads, 0, stream>>>(x, dy, y, save_mean, save_rstd, rows, cols, relu, rows_per_slab,
                                                                   partial);
   EFGB_LAUNCH_OK("bn::stats_partial_kernel");
-  bn::stats_final_bwd_kernel<<<(cols + 31) / 32, 256, 0, stream>>>(partial, slabs, cols, dbeta, dgamma);
+  bn::stats_final_bwd_kernel<<<(cols + bn::kFoldCols - 1) / bn::kFoldCols, 256, 0, stream>>>(partial, slabs, cols, dbeta, dgamma);
   EFGB_LAUNCH_OK("bn::stats_final_bwd_kernel");
   bn::apply_bwd_kernel<<<grid_for(rows * (cols / 4), bn::kThreads, kNumSMs * 8), bn::kThreads, 0, stream>>>(
       dy, x, y, save_mean, save_rstd, gamma, dbeta, dgamma, rows, cols, relu, dx, dres);
