@@ -401,6 +401,13 @@ def run_efgb200(args, backend=None):
                 if from_host:
                     b = [(t.to(dev, non_blocking=True), a) for t, a in b]
                 total = step(b)
+            if not from_host:
+                # bound the host's run-ahead to one step (what the asynchronous loss read does in the e2e arm): a host
+                # that free-runs until the driver's launch queue is full enqueues SLOWER (measured at N = 2 on one box:
+                # 57 ms of enqueue per step free-running, 38 ms throttled)
+                back_ev[i & 1].record()
+                if i >= 1:
+                    back_ev[(i - 1) & 1].synchronize()
             if from_host:
                 # D2H read of the step's result, one step behind the launches
                 back[i & 1][0:1].copy_(total.detach().reshape(1), non_blocking=True)
@@ -505,7 +512,7 @@ def run_efgb200(args, backend=None):
                    "conv_precision": ops.CONV_PRECISION if backend is None else "fp32 torch ops",
                    "cuda_graph": graph_state, "parallelism": "dp%d" % world,
                    "input_pipeline": ("index part of the next batch (H2D, voxelizer, strided rulebooks) on a side stream during "
-                                      "the current step; e2e loss read back asynchronously, one step behind") if prefetch else
+                                      "the current step; host run-ahead bounded to one step by an event wait (e2e: the asynchronous loss read)") if prefetch else
                                      "in line (no prefetch)",
                    "l2": "flushed before every timed step (256 MiB memset, inside the timed span)"},
         "e2e": {"value": round(e2e_value, 3), "unit": "scenes/s", "h2d_bytes_per_step": h2d_bytes,
