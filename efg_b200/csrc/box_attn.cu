@@ -590,8 +590,11 @@ static TileGeom tile_geom(int len_query, int query_grid_w, int64_t nw) {
 static bool use_tile_kernels(int len_value, int num_heads, int head_dim) {
   if (head_dim != 32) return false;
   if (static_cast<int64_t>(len_value) * num_heads * 32 >= (1ll << 31)) return false;  // 32-bit tap offsets
-  const char* e = getenv("EFGB_BOX_ATTN");
-  return !(e && strcmp(e, "generic") == 0);
+  static const bool generic = [] {   // read once per process (A/B measurements against the generic kernels)
+    const char* e = getenv("EFGB_BOX_ATTN");
+    return e && strcmp(e, "generic") == 0;
+  }();
+  return !generic;
 }
 
 static int check_args(int batch, int len_value, int num_heads, int head_dim, int num_levels, int len_query,

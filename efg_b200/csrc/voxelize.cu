@@ -47,6 +47,32 @@ __device__ __forceinline__ bool point_to_cell(const float* __restrict__ p, const
   return true;
 }
 
+// The xyz of the CTA's 256 consecutive points, read as coalesced 128-bit loads: the CTA's slice of the point array is one
+// contiguous block of 256 * nfeat floats (16-byte aligned when the array is), copied to shared memory with LDG.128 and
+// read back per point (row stride nfeat words).  A 5-float row is not 16-byte aligned, so per-point vector loads are not
+// possible; per-point scalar loads at a 20-byte stride touch every sector five times.
+constexpr int kStageFeat = 8;   // rows wider than this (or an unaligned array) take the scalar path
+__device__ __forceinline__ const float* stage_points(const float* __restrict__ points, int64_t n, int nfeat, float* s_pts,
+                                                     bool aligned) {
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * blockDim.x;
+  if (!aligned || nfeat > kStageFeat) {
+    __syncthreads();
+    return points + (base + threadIdx.x) * nfeat;
+  }
+  const int64_t left = n - base;
+  const int total = static_cast<int>(left < static_cast<int64_t>(blockDim.x) ? left : blockDim.x) * nfeat;
+  const float* src = points + base * nfeat;
+  for (int e = threadIdx.x * 4; e < total; e += blockDim.x * 4) {
+    if (e + 3 < total) {
+      *reinterpret_cast<float4*>(s_pts + e) = __ldg(reinterpret_cast<const float4*>(src + e));
+    } else {
+      for (int k = e; k < total; ++k) s_pts[k] = __ldg(src + k);
+    }
+  }
+  __syncthreads();
+  return s_pts + threadIdx.x * nfeat;
+}
+
 __device__ __forceinline__ int scene_of(const int32_t* __restrict__ offs, int batch, int64_t i) {
   int b = 0;
   while (b + 1 < batch && i >= offs[b + 1]) ++b;
@@ -56,14 +82,15 @@ __device__ __forceinline__ int scene_of(const int32_t* __restrict__ offs, int ba
 __global__ void __launch_bounds__(256)
 vox_insert_kernel(const float* __restrict__ points, int64_t n, int nfeat, const int32_t* __restrict__ offs, int batch,
                   VoxGeom g, uint32_t* __restrict__ pt_slot, uint32_t* tkeys, uint32_t* tfirst, uint32_t* thead,
-                  uint32_t* __restrict__ pt_next, uint32_t mask) {
+                  uint32_t* __restrict__ pt_next, uint32_t mask, int aligned) {
   __shared__ int32_t s_offs[kMaxBatch + 1];
+  __shared__ __align__(16) float s_pts[256 * kStageFeat];
   for (int t = threadIdx.x; t <= batch; t += blockDim.x) s_offs[t] = offs[t];
-  __syncthreads();
+  const float* mine = stage_points(points, n, nfeat, s_pts, aligned != 0);   // ends with __syncthreads()
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int c[3];
-  if (!point_to_cell(points + i * nfeat, g, c)) {
+  if (!point_to_cell(mine, g, c)) {
     pt_slot[i] = kEmpty;
     return;
   }
@@ -179,11 +206,14 @@ vox_emit_kernel(const float* __restrict__ points, int64_t n, int nfeat, const in
 }
 
 __global__ void __launch_bounds__(256)
-dynamic_voxelize_kernel(const float* __restrict__ points, int64_t n, int nfeat, VoxGeom g, int32_t* __restrict__ coors) {
+dynamic_voxelize_kernel(const float* __restrict__ points, int64_t n, int nfeat, VoxGeom g, int32_t* __restrict__ coors,
+                        int aligned) {
+  __shared__ __align__(16) float s_pts[256 * kStageFeat];
+  const float* mine = stage_points(points, n, nfeat, s_pts, aligned != 0);
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int c[3];
-  bool ok = point_to_cell(points + i * nfeat, g, c);
+  bool ok = point_to_cell(mine, g, c);
   coors[i * 3 + 0] = ok ? c[2] : -1;
   coors[i * 3 + 1] = ok ? c[1] : -1;
   coors[i * 3 + 2] = ok ? c[0] : -1;
@@ -266,7 +296,8 @@ extern "C" int efgb_hard_voxelize(const float* points, int64_t num_points, int n
   if (num_points > 0) {
     const unsigned nb = static_cast<unsigned>((num_points + 255) / 256);
     vox_insert_kernel<<<nb, 256, 0, stream>>>(points, num_points, num_features, scene_offsets, batch, g, pt_slot, tkeys,
-                                              tfirst, thead, pt_next, tsize - 1);
+                                              tfirst, thead, pt_next, tsize - 1,
+                                              (reinterpret_cast<uintptr_t>(points) & 15) == 0 ? 1 : 0);
     EFGB_LAUNCH_OK("vox_insert_kernel");
     vox_flag_kernel<<<nb, 256, 0, stream>>>(pt_slot, tfirst, num_points, flags);
     EFGB_LAUNCH_OK("vox_flag_kernel");
@@ -300,7 +331,8 @@ extern "C" int efgb_dynamic_voxelize(const float* points, int64_t num_points, in
   EFGB_REQUIRE(make_geom(voxel_size, coors_range, &g) == 0, EFGB_EINVAL, "dynamic_voxelize: empty grid");
   if (num_points == 0) return EFGB_OK;
   const unsigned nb = static_cast<unsigned>((num_points + 255) / 256);
-  dynamic_voxelize_kernel<<<nb, 256, 0, stream>>>(points, num_points, num_features, g, coors);
+  dynamic_voxelize_kernel<<<nb, 256, 0, stream>>>(points, num_points, num_features, g, coors,
+                                                  (reinterpret_cast<uintptr_t>(points) & 15) == 0 ? 1 : 0);
   EFGB_LAUNCH_OK("dynamic_voxelize_kernel");
   return EFGB_OK;
 }
