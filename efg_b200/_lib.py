@@ -55,6 +55,7 @@ SIGNATURES = {
     "efgb_sparse_to_dense": (_int, [_vp, _vp, _i64, _int, _int, _host_i32x3, _vp, _vp]),
     "efgb_dense_to_sparse": (_int, [_vp, _vp, _i64, _int, _int, _host_i32x3, _vp, _vp]),
     "efgb_augment_workspace_bytes": (_sz, [_i64]),
+    "efgb_paste_points": (_int, [_vp, _vp, _vp, _int, _i64, _vp, _i64, _int, _vp, _int, _vp, _vp]),
     "efgb_augment_points": (_int, [_vp, _i64, _int, _int, _int, ctypes.c_float, ctypes.c_float, ctypes.c_float, _host_f32, _host_f32,
                                    _vp, _vp, _vp, _sz, _vp]),
     "efgb_draw_gaussians": (_int, [_vp, _int, _int, _int, _vp, _vp]),

@@ -60,6 +60,51 @@ emit_kernel(const float* __restrict__ pts, int64_t n, int nfeat, Xform t, const 
   for (int f = 3; f < nfeat; ++f) o[f] = pts[i * nfeat + f];
 }
 
+
+// GT-database paste (DatabaseSampling.__call__, efg/data/augmentations/extend_3d.py:68-92): the output is
+// [points of the accepted database objects, translated to their boxes | scene points].  `table[k]` = (first point of
+// object k in the resident database, first output row, point count); `planes` (optional, rm_points_after_sample) are the
+// inward-pointing face planes of the pasted boxes as the reference builds them (box_ops.py:285-310): a scene point inside
+// any box (all six signs < 0, box_ops.py:356-371, evaluated left to right without contraction) is not compacted away but
+// moved out of every detection range (kPasteDropped), where the voxelizer drops it — same voxels, no count to read back.
+constexpr float kPasteDropped = 1e30f;
+
+__global__ void __launch_bounds__(256)
+paste_points_kernel(const float* __restrict__ db, const int32_t* __restrict__ table, const float* __restrict__ centers, int num_obj,
+                    int64_t n_paste, const float* __restrict__ scene, int64_t n_scene, int nfeat,
+                    const float* __restrict__ planes, int num_rm, float* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_paste + n_scene) return;
+  float* dst = out + i * nfeat;
+  if (i < n_paste) {
+    int lo = 0, hi = num_obj - 1;
+    while (lo < hi) {   // last object whose first output row is <= i
+      const int mid = (lo + hi + 1) >> 1;
+      if (__ldg(table + mid * 3 + 1) <= i) lo = mid; else hi = mid - 1;
+    }
+    const float* src = db + (static_cast<int64_t>(__ldg(table + lo * 3)) + (i - __ldg(table + lo * 3 + 1))) * nfeat;
+    for (int f = 0; f < nfeat; ++f) dst[f] = f < 3 ? __fadd_rn(__ldg(src + f), __ldg(centers + lo * 3 + f)) : __ldg(src + f);
+    return;
+  }
+  const float* src = scene + (i - n_paste) * nfeat;
+  float x = __ldg(src), y = __ldg(src + 1), z = __ldg(src + 2);
+  bool inside_any = false;
+  for (int m = 0; m < num_rm && !inside_any; ++m) {
+    bool inside = true;
+    for (int k = 0; k < 6 && inside; ++k) {
+      const float4 pl = __ldg(reinterpret_cast<const float4*>(planes) + m * 6 + k);
+      const float sign = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, pl.x), __fmul_rn(y, pl.y)), __fmul_rn(z, pl.z)), pl.w);
+      inside = !(sign >= 0.f);
+    }
+    inside_any = inside;
+  }
+  if (inside_any) x = y = z = kPasteDropped;
+  dst[0] = x;
+  dst[1] = y;
+  dst[2] = z;
+  for (int f = 3; f < nfeat; ++f) dst[f] = __ldg(src + f);
+}
+
 }  // namespace aug
 }  // namespace efgb
 
@@ -104,5 +149,22 @@ extern "C" int efgb_augment_points(const float* points, int64_t n, int nfeat, in
   if (rc != EFGB_OK) return rc;
   aug::emit_kernel<<<grid_for(n, 256, 1 << 30), 256, 0, stream>>>(points, n, nfeat, t, pos, out_points, out_count);
   EFGB_LAUNCH_OK("aug::emit_kernel");
+  return EFGB_OK;
+}
+
+extern "C" int efgb_paste_points(const float* db_points, const int32_t* obj_table, const float* obj_centers, int num_obj,
+                                 int64_t n_paste, const float* scene_points, int64_t n_scene, int nfeat, const float* planes,
+                                 int num_rm_boxes, float* out_points, efgb_stream_t stream_) {
+  cudaStream_t stream = as_stream(stream_);
+  EFGB_REQUIRE(num_obj >= 0 && n_paste >= 0 && n_scene >= 0 && nfeat >= 3 && num_rm_boxes >= 0, EFGB_EINVAL, "paste_points: bad argument");
+  const int64_t total = n_paste + n_scene;
+  if (total == 0) return EFGB_OK;
+  EFGB_REQUIRE(out_points && (n_scene == 0 || scene_points) && (n_paste == 0 || (db_points && obj_table && obj_centers && num_obj > 0)) &&
+                   (num_rm_boxes == 0 || (planes && (reinterpret_cast<uintptr_t>(planes) & 15) == 0)),
+               EFGB_EINVAL, "paste_points: null or misaligned pointer");
+  aug::paste_points_kernel<<<grid_for(total, 256, 1 << 30), 256, 0, stream>>>(db_points, obj_table, obj_centers, num_obj, n_paste,
+                                                                             scene_points, n_scene, nfeat, planes, num_rm_boxes,
+                                                                             out_points);
+  EFGB_LAUNCH_OK("aug::paste_points_kernel");
   return EFGB_OK;
 }

@@ -268,6 +268,17 @@ int efgb_augment_points(const float* points, int64_t n, int nfeat, int flip_x, i
                         float* out_points, int32_t* out_count, void* workspace, size_t workspace_bytes,
                         efgb_stream_t stream);
 
+/* GT-database paste on the device (DatabaseSampling.__call__, efg/data/augmentations/extend_3d.py:68-92; the sampling and
+ * the collision test stay host logic over <= 100 boxes, efg/data/samplers/gt_database_sampler.py:111-212).
+ * out_points [n_paste + n_scene, nfeat] = [database points of the accepted objects, xyz translated by obj_centers |
+ * scene points].  obj_table [num_obj, 3] int32 on the device = (first point in db_points, first output row, count), rows
+ * in output order.  planes (nullable; rm_points_after_sample): [num_rm_boxes, 6, 4] inward face planes (normal, d) of the
+ * pasted boxes (box_ops.py:285-310); scene points inside a box get xyz = 1e30 (dropped by any range check / the
+ * voxelizer) instead of being compacted away: no count has to be read back. */
+int efgb_paste_points(const float* db_points, const int32_t* obj_table, const float* obj_centers, int num_obj,
+                      int64_t n_paste, const float* scene_points, int64_t n_scene, int nfeat,
+                      const float* planes /* nullable */, int num_rm_boxes, float* out_points, efgb_stream_t stream);
+
 /* CenterPoint label assignment, heatmap part (CP/voxelnet.py:44-192, CP/center_utils.py:29-58): objects[i] = (plane, x, y,
  * radius) int32 on the device; heatmaps [planes, height, width] f32, zero-initialised by the caller; every object's
  * Gaussian (sigma = (2 r + 1) / 6) is max-ed into its plane.  Replaces the host numpy drawing + upload of the maps. */
