@@ -89,5 +89,6 @@ def dn_post_process(outputs_class, outputs_coord, dn_meta, aux_loss):
         if aux_loss:
             out["aux_outputs"] = [{"pred_logits": a, "pred_boxes": b} for a, b in zip(known_cls[:-1], known_box[:-1])]
         dn_meta["output_known_lbs_bboxes"] = out
+        dn_meta["known_stack"] = (known_cls, known_box)   # the layer-stacked tensors, for the all-layers-at-once losses
         outputs_class, outputs_coord = outputs_class[:, :, pad:], outputs_coord[:, :, pad:]
     return outputs_class, outputs_coord

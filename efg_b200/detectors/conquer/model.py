@@ -207,7 +207,13 @@ class ConQueR(VoxelDETR):
         dec_out = {"pred_logits": cls_out[-1][:, :nq], "pred_boxes": box_out[-1][:, :nq],
                    "aux_outputs": [{"pred_logits": a[:, :nq], "pred_boxes": b[:, :nq]}
                                    for a, b in zip(cls_out[:-1], box_out[:-1])]}
-        mats = prop.losses.prepare(enc_out, bin_targets) + head.losses.prepare(dec_out, targets)
+        stacked = self.stacked_losses and isinstance(targets, TargetList) and targets.labels_cat is not None
+        cls_q, box_q = cls_out[:, :, :nq], box_out[:, :, :nq]
+        if stacked:   # all decoder layers at once (see VoxelDETR.losses): L-fold fewer launches in a host-bound step
+            dec_mats = head.losses.matcher.cost_matrices_stacked(cls_q, box_q, targets)
+        else:
+            dec_mats = head.losses.prepare(dec_out, targets)
+        mats = prop.losses.prepare(enc_out, bin_targets) + dec_mats
         matcher = head.losses.matcher
         if self.device_matching and mats and mats[0].is_cuda and "solve" not in matcher.__dict__:
             matches = device_matches(mats, len(mats) // max(len(targets), 1), targets.offsets, cls_out.device)  # csrc/lsa.cu
@@ -217,13 +223,14 @@ class ConQueR(VoxelDETR):
             per_layer = [solved[i * bs:(i + 1) * bs] for i in range(len(solved) // max(bs, 1))]
             matches = upload_matches(per_layer, targets.offsets, cls_out.device)
         losses = {k + "_enc": v for k, v in prop.compute_losses(enc_out, bin_targets, num_boxes, solved=matches[:1]).items()}
-        losses.update(head.compute_losses(dec_out, targets, num_boxes, solved=matches[1:]))
-        if dn_meta is not None:
-            losses.update(self.dn_losses(head, dn_meta, targets, num_boxes))
+        if dn_meta is not None:   # before the matching losses: both leave their last-layer logits on the loss object
+            losses.update(self.dn_losses(head, dn_meta, targets, num_boxes, stacked))
+        losses.update(head.compute_losses(dec_out, targets, num_boxes, solved=matches[1:],
+                                          stacked=(cls_q, box_q) if stacked else None))
         losses.update(self.contrastive_losses(cls_out, box_out, matches[-1], targets, dn_meta))
         return losses
 
-    def dn_losses(self, head, dn_meta, targets, num_boxes):
+    def dn_losses(self, head, dn_meta, targets, num_boxes, stacked=False):
         """Losses of the positively noised queries against their own GT (CQ/losses.py:154-207).  The reference
         builds the target index as ``arange(0, len(labels) - 1)`` — the LAST ground-truth box of every scene is
         left out; kept as is for identical results."""
@@ -251,6 +258,16 @@ class ConQueR(VoxelDETR):
         weights = head.losses.weight_dict
         out = {}
         layers = list(known.get("aux_outputs", [])) + [{k: v for k, v in known.items() if k != "aux_outputs"}]
+        if stacked and "known_stack" in dn_meta:
+            # the same target index for every layer: all layers in one pass (Det3DLoss.finish_stacked)
+            k_cls, k_box = dn_meta["known_stack"]
+            L = k_cls.shape[0]
+            per = head.losses.finish_stacked(k_cls, k_box, targets, [match] * L, num_boxes * groups)
+            for key, v in per.items():
+                base, _, li = key.rpartition("_")
+                name, suffix = (base, "_dn_" + li) if li.isdigit() else (key, "_dn")
+                out[name + suffix] = v * weights.get(name + suffix, 1.0)
+            return out
         for li, lo in enumerate(layers):
             suffix = "_dn" if li == len(layers) - 1 else "_dn_{}".format(li)
             for loss in head.losses.losses:
@@ -279,16 +296,18 @@ class ConQueR(VoxelDETR):
         neg_mask = torch.ones(B, nq, dtype=torch.bool, device=dev)
         neg_mask[b_idx, q_idx] = False
         pos_rows = local_t[:, None] + max_gt * torch.arange(1, groups + 1, device=dev)[None, :]  # [P, groups]
-        for li in range(cls_out.shape[0]):
-            projs = torch.cat((cls_out[li], box_out[li]), dim=-1)
-            gt_projs = F.normalize(self.projector(projs[:, nq:].detach()), dim=-1, eps=1e-8)
-            pred_projs = F.normalize(self.predictor(self.projector(projs[:, :nq])), dim=-1, eps=1e-8)
-            sim = torch.einsum("bgc,bqc->bgq", gt_projs, pred_projs) / self.tau      # [B, G, nq]
-            rows = sim[b_idx[:, None], pos_rows]                                     # [P, groups, nq]
-            pos = torch.gather(rows, 2, q_idx[:, None, None].expand(-1, groups, 1))  # [P, groups, 1]
-            neg = (torch.exp(rows) * neg_mask[b_idx][:, None, :]).sum(-1, keepdim=True)
-            loss = torch.log(torch.exp(pos) + neg) - pos
-            out["loss_contrastive_dec_{}".format(li)] = self.contras_loss_coeff * loss.mean(dim=1).sum() / num_gts
+        L = cls_out.shape[0]
+        projs = torch.cat((cls_out, box_out), dim=-1)                                # [L, B, nq + G, 10]
+        gt_projs = F.normalize(self.projector(projs[:, :, nq:].detach()), dim=-1, eps=1e-8)
+        pred_projs = F.normalize(self.predictor(self.projector(projs[:, :, :nq])), dim=-1, eps=1e-8)
+        sim = torch.einsum("lbgc,lbqc->lbgq", gt_projs, pred_projs) / self.tau       # [L, B, G, nq]
+        rows = sim[:, b_idx[:, None], pos_rows]                                      # [L, P, groups, nq]
+        pos = torch.gather(rows, 3, q_idx[None, :, None, None].expand(L, -1, groups, 1))
+        neg = (torch.exp(rows) * neg_mask[b_idx][None, :, None, :]).sum(-1, keepdim=True)
+        loss = torch.log(torch.exp(pos) + neg) - pos                                 # [L, P, groups, 1]
+        per_layer = self.contras_loss_coeff * loss.mean(dim=2).sum((1, 2)) / num_gts
+        for li in range(L):
+            out["loss_contrastive_dec_{}".format(li)] = per_layer[li]
         return out
 
     def postprocess_threshold(self, logits, boxes):
