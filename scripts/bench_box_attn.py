@@ -48,3 +48,37 @@ for name, lq, grid in (("encoder", hh * ww, True), ("decoder", 300, False)):
     print("%-10s %7d  fwd  %9.1f  %8.1f" % (name, lq, us, fb / us / 1e3))
     us = timeit(lambda: ops.box_attn_backward(value, shapes, start, loc, attn, go))
     print("%-10s %7d  bwd  %9.1f  %8.1f" % (name, lq, us, bb / us / 1e3))
+
+# the fused operator (sampling grid + softmax inside the attention kernels) on a projection output that yields the same
+# boxes as above: logits random, offsets ~ U[0, 1) like linear_box_bias at initialisation
+from efg_b200 import _lib
+import ctypes
+L = _lib.lib()
+for nv in (4,):
+    lq = hh * ww
+    n_attn, n_box = H * P, H * nv
+    ld = (n_attn + n_box + 63) // 64 * 64
+    proj = torch.zeros(B, lq, ld, device=dev)
+    proj[..., :n_attn] = torch.randn(B, lq, n_attn, device=dev)
+    proj[..., n_attn:n_attn + n_box] = torch.rand(B, lq, n_box, device=dev)
+    ys, xs = torch.meshgrid(torch.linspace(0.5, hh - 0.5, hh, device=dev) / hh, torch.linspace(0.5, ww - 0.5, ww, device=dev) / ww, indexing="ij")
+    ref = torch.zeros(B, lq, 7, device=dev)
+    ref[..., 0], ref[..., 1] = xs.reshape(-1), ys.reshape(-1)
+    ref[..., 2] = ref[..., 5] = 0.5
+    ref[..., 3:5] = 0.025
+    out = torch.empty(B, lq, H * C, device=dev)
+    go = torch.randn(B, lq, H * C, device=dev)
+    gv, gp = torch.empty_like(value), torch.empty_like(proj)
+    off = ctypes.c_void_p(proj.data_ptr() + 4 * n_attn)
+    goff = ctypes.c_void_p(gp.data_ptr() + 4 * n_attn)
+    st = ops._stream()
+    fwd = lambda: L.efgb_box_attn_fused_forward(ops._p(value), ops._p(shapes), ops._p(start), off, ops._p(proj), ops._p(ref), ops._p(kidx),
+                                                B, hh * ww, H, lq, P, nv, ld, ld, ww, ops._p(out), st)
+    bwd = lambda: L.efgb_box_attn_fused_backward(ops._p(value), ops._p(shapes), ops._p(start), off, ops._p(proj), ops._p(ref), ops._p(kidx),
+                                                 ops._p(go), B, hh * ww, H, lq, P, nv, ld, ld, ww, ops._p(gv), goff, ops._p(gp), st)
+    fb = 4 * (value.numel() + B * lq * (n_attn + n_box) + out.numel())
+    bb = 4 * (2 * value.numel() + 2 * B * lq * (n_attn + n_box) + go.numel())
+    us = timeit(fwd)
+    print("%-10s %7d  fwd  %9.1f  %8.1f   [fused grid + softmax]" % ("encoder", lq, us, fb / us / 1e3))
+    us = timeit(bwd)
+    print("%-10s %7d  bwd  %9.1f  %8.1f   [fused grid + softmax]" % ("encoder", lq, us, bb / us / 1e3))
