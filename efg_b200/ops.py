@@ -394,7 +394,7 @@ def packed_weights(w_param, mode, split):
     if same:
         hit[0] = ver
         return packed
-    if len(_PACK_CACHE) >= _PACK_CACHE_MAX:
+    if len(_PACK_CACHE) >= _PACK_CACHE_MAX and not _PACK_PINNED:   # (pinned by captured graphs: grows instead)
         clear_pack_cache()
     _PACK_JOBS.clear()   # the key may have had another image
     _PACK_CACHE[key] = [ver, packed, weakref.ref(base), w_param.detach()]
