@@ -321,6 +321,8 @@ def run_efgb200(args, backend=None):
     # stream").  Every event below is recorded on this stream.
     torch.cuda.set_stream(torch.cuda.Stream(device=dev))
     torch.manual_seed(0)
+    # the dense 2-D convolutions of the FPN / RPN are cuDNN library calls on fixed shapes: let cuDNN pick its algorithm
+    torch.backends.cudnn.benchmark = bool(int(os.environ.get("EFGB_CUDNN_BENCHMARK", "1")))
     if args.workload == "config1":
         return run_config1(args, dev)
 
