@@ -470,7 +470,10 @@ def run_efgb200(args, backend=None):
     sampler = ClockSampler(local_rank) if rank == 0 and not os.environ.get("EFGB_BENCH_NO_CLOCKS") else None
     ms_dev, _ = timed(resident, args.steps, from_host=False, sampler=sampler)
     clocks = sampler.result() if sampler is not None else None
-    launches = _lib.lib().efgb_launch_count() - launches0
+    launches_eager = _lib.lib().efgb_launch_count() - launches0
+    # kernels inside the CUDA graphs are launched by the replay, not by a host call: counted at capture time, per replay
+    launches_graph = int(getattr(model, "static_graph_launches", 0) or 0) * args.steps if graph_state.startswith(("static", "encoder")) else 0
+    launches = launches_eager + launches_graph
     ms_e2e, last_loss = timed(pinned, args.steps, from_host=True)
 
     scenes_total = args.scenes * world * args.steps
@@ -525,6 +528,7 @@ def run_efgb200(args, backend=None):
         "e2e": {"value": round(e2e_value, 3), "unit": "scenes/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": last_loss},
         "gpu_launches": int(launches),
+        "gpu_launches_detail": {"host_launched": int(launches_eager), "replayed_from_cuda_graphs": int(launches_graph)},
         "host_enqueue_ms_per_step": round(host_ms[0], 3),   # Python + launch time of a step (no synchronisation inside)
         "clocks": clocks,
     }

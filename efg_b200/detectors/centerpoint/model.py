@@ -142,7 +142,9 @@ class VoxelNet(nn.Module):
             flat = [t for k in self._TARGET_KEYS for t in targets[k]]
             sample = (bev.detach().clone().requires_grad_(True),) + tuple(t.clone() for t in flat)
             torch.cuda.synchronize()
+            count0 = ops.launch_count()
             self._static_call = torch.cuda.make_graphed_callables(section, sample, allow_unused_input=True)
+            self.static_graph_launches = (ops.launch_count() - count0) // 4   # library kernels per replay (none: cuDNN / ATen only)
             self._static_section = [section]
             self._static_batch = len(batched_inputs)
             return True

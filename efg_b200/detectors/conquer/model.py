@@ -140,10 +140,12 @@ class ConQueR(VoxelDETR):
             sample = tuple(feats[n].detach().clone().requires_grad_(True) for n in names)
             torch.cuda.synchronize()
             ops.PACKS_REFRESHED_PER_STEP = True   # see VoxelDETR.enable_static_graph
+            count0 = ops.launch_count()
             try:
                 self._static_call = torch.cuda.make_graphed_callables(section, sample, allow_unused_input=True)
             finally:
                 ops.PACKS_REFRESHED_PER_STEP = False
+            self.static_graph_launches = (ops.launch_count() - count0) // 4
             self._static_packs = ops.pin_pack_cache()
             self._static_names, self._static_batch = names, len(batched_inputs)
             self._static_section = [section]

@@ -273,10 +273,14 @@ class VoxelDETR(nn.Module):
             # weight images: the captured kernels read the cached images, which forward() refreshes in one launch
             # before every replay (ops.refresh_packs) instead of one captured pack kernel per layer and direction
             ops.PACKS_REFRESHED_PER_STEP = True
+            count0 = ops.launch_count()
             try:
                 self._static_call = torch.cuda.make_graphed_callables(section, sample, allow_unused_input=True)
             finally:
                 ops.PACKS_REFRESHED_PER_STEP = False
+            # library kernels one replay (forward + backward graph) executes: make_graphed_callables runs the section
+            # three times eagerly and once under capture
+            self.static_graph_launches = (ops.launch_count() - count0) // 4
             self._static_packs = ops.pin_pack_cache()   # the graphs hold raw pointers into these images
             self._static_names, self._static_batch = names, len(batched_inputs)
             self._static_section = [section]

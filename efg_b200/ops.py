@@ -68,6 +68,12 @@ class KernelProfiler:
 
 PROFILER = None
 
+
+def launch_count():
+    """Kernels this library has launched in the process so far (a host-side counter: launches recorded into a CUDA graph
+    count once, at capture time)."""
+    return int(_lib.lib().efgb_launch_count())
+
 _workspaces = {}
 
 
