@@ -17,6 +17,7 @@ with CUDA events in-situ; cpu_baseline = the oracle-backed model on the host cor
 sample (one scene).
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -385,6 +386,10 @@ def run_efgb200(args, backend=None):
                 raise ValueError("matrix contains invalid numeric entries (device linear_sum_assignment)")
             return float(back[i & 1][0])
 
+        # Python's cyclic collector is scheduled by hand, as large-scale trainers do: a generation-2 pass over the autograd
+        # objects of a step takes tens of ms and lands in whichever timed region happens to trigger it
+        gc.collect()
+        gc.disable()
         barrier()
         if sampler is not None:
             sampler.start()
@@ -426,6 +431,7 @@ def run_efgb200(args, backend=None):
         if sampler is not None:
             sampler.stop()  # the device is still executing the tail of the last step
         barrier()
+        gc.enable()
         ms = ev0.elapsed_time(ev1)
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)

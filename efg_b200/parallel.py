@@ -75,8 +75,8 @@ class GradAverager:
         if cur:
             self._make_bucket(cur)
         # the hooks also run in a single process: they are how "received a gradient" is known (hide_unused)
-        for p in self.params:
-            p.register_post_accumulate_grad_hook(self._on_grad)
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self._unused = None        # parameters hide_unused() detaches (known after the first step)
 
     def _make_bucket(self, params):
         p0 = params[0]
@@ -96,11 +96,18 @@ class GradAverager:
         for b in self.buckets:
             b.flat.zero_()
             b.arrived, b.handle, b.launched = 0, None, False
-            off = 0
-            for p in b.params:
-                if p.grad is None or p.grad.data_ptr() != b.flat.data_ptr() + off * b.flat.element_size():
-                    p.grad = b.flat[off:off + p.numel()].view_as(p)
-                off += p.numel()
+        if self._unused is not None:
+            # steady state: only the parameters hide_unused() detached need their view back (nothing else replaces a
+            # gradient: the optimizer and autograd write through the views)
+            for p, view in self._unused:
+                p.grad = view
+        else:
+            for b in self.buckets:
+                off = 0
+                for p in b.params:
+                    if p.grad is None or p.grad.data_ptr() != b.flat.data_ptr() + off * b.flat.element_size():
+                        p.grad = b.flat[off:off + p.numel()].view_as(p)
+                    off += p.numel()
         self._fired.clear()
 
     def _on_grad(self, p):
@@ -118,6 +125,10 @@ class GradAverager:
         b.arrived += 1
         if self._used is not None and self.world > 1 and self.overlap and b.arrived == b.expected and not b.launched:
             self._launch(b)
+
+    def _on_late_grad(self, p):
+        self._used.add(id(p))
+        self._unused = [(q, v) for q, v in self._unused if q is not p]
 
     def _launch(self, b):
         b.launched = True
@@ -150,12 +161,31 @@ class GradAverager:
             self._used = set(self._fired)
             for b in self.buckets:
                 b.expected = sum(1 for p in b.params if id(p) in self._used)
+            if self.world == 1:
+                # a single process has nothing to launch from the hooks: they were only needed to learn which parameters
+                # receive gradients (262 Python calls per backward otherwise)
+                for h in self._hooks:
+                    h.remove()
+                self._hooks = []
+                self._unused = []
+                for b in self.buckets:
+                    off = 0
+                    for p in b.params:
+                        if id(p) not in self._used:
+                            self._unused.append((p, b.flat[off:off + p.numel()].view_as(p)))
+                            # a parameter that starts to receive gradients later is used from then on
+                            self._hooks.append(p.register_post_accumulate_grad_hook(self._on_late_grad))
+                        off += p.numel()
         self._steps += 1
 
     def hide_unused(self):
         """Set ``grad = None`` on the parameters that got no gradient in the first step (DDP leaves them None, so the
         optimizer skips them); zero_grad() re-attaches the views.  Call between finish() and optimizer.step()."""
         if self._used is None:
+            return
+        if self._unused is not None:
+            for p, _ in self._unused:
+                p.grad = None
             return
         for p in self.params:
             if id(p) not in self._used:
