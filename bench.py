@@ -386,11 +386,8 @@ def run_efgb200(args, backend=None):
                 raise ValueError("matrix contains invalid numeric entries (device linear_sum_assignment)")
             return float(back[i & 1][0])
 
-        # Python's cyclic collector is scheduled by hand, as large-scale trainers do: a generation-2 pass over the autograd
-        # objects of a step takes tens of ms and lands in whichever timed region happens to trigger it
-        gc.collect()
-        gc.disable()
-        barrier()
+        gc.collect()   # start every timed region from the same collector state (the collector itself stays on: the autograd
+        barrier()      # objects of a step hold device memory through reference cycles, and without it the allocator grows)
         if sampler is not None:
             sampler.start()
         ev0.record()
@@ -431,7 +428,6 @@ def run_efgb200(args, backend=None):
         if sampler is not None:
             sampler.stop()  # the device is still executing the tail of the last step
         barrier()
-        gc.enable()
         ms = ev0.elapsed_time(ev1)
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
