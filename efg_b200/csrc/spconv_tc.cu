@@ -543,7 +543,7 @@ __device__ __forceinline__ void produce_a_wide(const Params& p, const CtaWork& w
 
 // A producers over a PRE-SPLIT input (bf16x3, sparse convolutions).  A gathered input row is used by ~14 output rows, so
 // splitting fp32 -> bf16 hi / lo inside the producers repeats the conversion 14 times and was what bound the kernel
-// (issue slots: ~90 instructions per 16-byte piece of the A tile, profiles/r2_ncu_spconv_regpath.txt).  Here the input has
+// (issue slots: ~90 instructions per 16-byte piece of the A tile, profiles/r2_ncu_full_spconv_planes_before_mma_fix.txt).  Here the input has
 // been split once into `planes[row] = [hi c_red x bf16 | lo c_red x bf16]` (same bytes per row as fp32) and a piece of
 // the A tile is ONE cp.async (LDGSTS, zero-fill for a missing neighbour): no registers, no conversion, ~10 instructions
 // per piece, kDepth stages of gathers in flight per thread.
