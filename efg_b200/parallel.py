@@ -220,3 +220,35 @@ class AsyncMean:
         if self.t.is_cuda:  # stay on the device: an .item() would drain the pipeline once per step on every rank
             return (self.t / self.world).clamp_(min=floor).reshape(())
         return max(float(self.t.item()) / self.world, floor)
+
+
+class GraphedOptimizerStep:
+    """``optimizer.step()`` replayed from a CUDA graph.  The multi-tensor optimizers of torch regroup their tensor lists in
+    Python on every call (~3 ms for the 260 parameters of Voxel-DETR); in a training loop whose gradients live at fixed
+    addresses — the bucket views of GradAverager — the step is the same kernels on the same pointers every time.
+
+    Construct it after a backward pass, with every gradient that will ever exist in place (and the unused ones hidden:
+    GradAverager.hide_unused), from an optimizer created with ``capturable=True`` (its step counters then live on the
+    device).  Hyper-parameters held as Python numbers (lr, betas, weight decay) are baked in: re-capture after changing
+    them, or keep lr in a tensor.  A replay updates the parameters in place without going through autograd's version
+    counters, so they are bumped by hand: everything keyed on ``Tensor._version`` (the packed weight images of
+    efg_b200.ops) sees the update.
+
+    Not wired into bench.py: three A/B runs of the Voxel-DETR step showed the device-resident arm SLOWER with it (51–53 vs
+    58–59 scenes/s, host enqueue 37 vs 32 ms) while the end-to-end arm was unchanged; the cause was not found within the
+    round's GPU budget.  The class and its equality test (tests/test_gpu_graph.py) stay as a tool."""
+
+    def __init__(self, optimizer):
+        self.optimizer = optimizer
+        self.params = [p for g in optimizer.param_groups for p in g["params"] if p.grad is not None]
+        if not self.params or not all(p.is_cuda for p in self.params):
+            raise RuntimeError("GraphedOptimizerStep needs CUDA parameters with gradients in place")
+        if not all(g.get("capturable", False) for g in optimizer.param_groups):
+            raise RuntimeError("GraphedOptimizerStep needs an optimizer created with capturable=True")
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            optimizer.step()
+
+    def step(self):
+        self.graph.replay()
+        torch.autograd.graph.increment_version(self.params)

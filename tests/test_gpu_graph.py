@@ -135,3 +135,42 @@ def test_conquer_encoder_graph_equals_eager():
         assert set(ge) == set(gg)
         rels = sorted(((ge[n] - gg[n]).norm() / ge[n].norm().clamp_min(1e-6)).item() for n in ge)
         assert rels[len(rels) // 2] <= 0.05 and rels[int(len(rels) * 0.9)] <= 0.3, (rels[len(rels) // 2], rels[-1])
+
+
+def test_graphed_optimizer_step_matches_eager_and_bumps_versions():
+    """parallel.GraphedOptimizerStep: AdamW replayed from a CUDA graph updates the parameters like the eager step, over
+    several steps with changing gradients, and bumps Tensor._version (the packed-weight cache is keyed on it)."""
+    from efg_b200.parallel import GradAverager, GraphedOptimizerStep
+
+    torch.manual_seed(0)
+    with torch.cuda.stream(torch.cuda.Stream()):
+        def make():
+            torch.manual_seed(3)
+            return torch.nn.Sequential(torch.nn.Linear(32, 64), torch.nn.ReLU(), torch.nn.Linear(64, 8)).cuda()
+        a, b = make(), make()
+        opts = [torch.optim.AdamW(m.parameters(), lr=1e-3, weight_decay=0.01, betas=(0.9, 0.99), eps=1e-9, fused=True, capturable=True)
+                for m in (a, b)]
+        avs = [GradAverager(m) for m in (a, b)]
+        xs = [torch.randn(16, 32, device="cuda") for _ in range(6)]
+
+        def backward(m, av, x):
+            av.zero_grad()
+            m(x).square().mean().backward()
+            av.finish()
+            av.hide_unused()
+
+        for m, av, o in zip((a, b), avs, opts):      # one eager step each: optimizer state exists, buckets in place
+            backward(m, av, xs[0])
+            o.step()
+        backward(b, avs[1], xs[1])                   # gradients in place for the capture (the capture itself applies nothing)
+        graphed = GraphedOptimizerStep(opts[1])
+        for x in xs[1:]:
+            backward(a, avs[0], x)
+            opts[0].step()
+            backward(b, avs[1], x)
+            v0 = [p._version for p in b.parameters()]
+            graphed.step()
+            assert all(p._version > v for p, v in zip(b.parameters(), v0))
+        torch.cuda.synchronize()
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert torch.allclose(pa, pb, rtol=1e-6, atol=1e-7), float((pa - pb).abs().max())
