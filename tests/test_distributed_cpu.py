@@ -77,3 +77,50 @@ def test_two_rank_gradient_average_matches_single_process(tmp_path):
     (0.5 * (model(data[0]).square().mean() + model(data[1]).square().mean())).backward()
     for p, g in zip(model.parameters(), r0["grads"]):
         assert torch.allclose(p.grad, g, atol=1e-6)
+
+
+def test_grad_averager_single_process_drops_its_hooks_and_follows_late_parameters():
+    """world size 1: after the first step the per-parameter hooks are gone (they only taught which parameters receive
+    gradients), unused parameters keep grad = None towards the optimizer, and a parameter that starts to receive
+    gradients later is used from then on."""
+    import torch
+    from efg_b200.parallel import GradAverager
+
+    torch.manual_seed(0)
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.b = torch.nn.Linear(4, 4), torch.nn.Linear(4, 4)
+            self.use_b = False
+
+        def forward(self, x):
+            y = self.a(x)
+            return self.b(y) if self.use_b else y
+
+    net = Net()
+    av = GradAverager(net)
+    x = torch.randn(3, 4)
+    seen = []
+    for step in range(4):
+        if step == 2:
+            net.use_b = True
+        av.zero_grad()
+        net(x).sum().backward()
+        av.finish()
+        av.hide_unused()
+        seen.append([p.grad is not None for p in net.parameters()])
+        # gradients are the bucket views (the optimizer and the all-reduce share them)
+        for b in av.buckets:
+            for p in b.params:
+                if p.grad is not None:
+                    assert p.grad.untyped_storage().data_ptr() == b.flat.untyped_storage().data_ptr()
+    assert seen[0] == [True, True, False, False] and seen[1] == seen[0]
+    assert seen[2] == [True, True, True, True] and seen[3] == seen[2]
+    assert len(av._hooks) == 2          # only the two parameters that were unused in the first step are still watched
+    ref = Net()
+    ref.load_state_dict(net.state_dict())
+    ref.use_b = True
+    ref(x).sum().backward()
+    for p, q in zip(net.parameters(), ref.parameters()):
+        assert torch.allclose(p.grad, q.grad)
