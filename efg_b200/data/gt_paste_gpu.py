@@ -100,6 +100,35 @@ def box_planes(boxes):
     return out
 
 
+class BatchSampler:
+    """Order in which database entries of one class are handed out (gt_database_sampler.py:16-66): a shuffled index list,
+    padded to a multiple of the world size and sharded by rank, consumed `num` at a time; when fewer than `num + 1`
+    entries are left the rest is returned (possibly fewer than asked for) and the shard is reshuffled.  Draws from
+    `np.random` exactly as the reference does, so a seeded run picks the same objects."""
+
+    def __init__(self, n, shuffle=True, rank=0, world=1):
+        self.num_samples = int(np.ceil(n * 1.0 / world))
+        total = self.num_samples * world
+        indices = np.arange(n).tolist()
+        if shuffle:
+            np.random.shuffle(indices)
+        indices += indices[:(total - n)]
+        self._indices = indices[self.num_samples * rank:self.num_samples * (rank + 1)]
+        self._idx = 0
+        self._shuffle = shuffle
+
+    def sample(self, num):
+        if self._idx + num >= self.num_samples:
+            ret = self._indices[self._idx:].copy()
+            if self._shuffle:
+                np.random.shuffle(self._indices)
+            self._idx = 0
+        else:
+            ret = self._indices[self._idx:self._idx + num]
+            self._idx += num
+        return ret
+
+
 class GpuGtDatabase:
     """`groups`: the reference's sample_groups, e.g. [{"VEHICLE": 15}, {"PEDESTRIAN": 10}];  `db`: {class: [info, ...]}
     with info = {"box3d_lidar": [7], "points": [n, F] float32, ...} (points relative to the box centre, as stored by the
@@ -125,6 +154,12 @@ class GpuGtDatabase:
         self.points = torch.from_numpy(packed).to(self.device)      # resident for the whole run
         self._cursor = {name: 0 for name in self.classes}
         self._pick = pick or self._in_order
+
+    def use_reference_sampling(self, rank=0, world=1, shuffle=True):
+        """Hand out entries like the reference's per-class BatchSampler (shuffled, sharded by rank; draws np.random)."""
+        samplers = {name: BatchSampler(self.boxes[name].shape[0], shuffle, rank, world) for name in self.classes}
+        self._pick = lambda name, num: samplers[name].sample(num)
+        return self
 
     @classmethod
     def from_infos(cls, db_infos, root_path, groups, device, points_dim, min_points=0, difficulty=-1, pick=None):
